@@ -34,6 +34,11 @@ class OracleEncoderOutput:
     def shape(self):
         return tuple(self.enc.shape)
 
+    def select(self, indices):
+        idx = torch.as_tensor(list(indices), dtype=torch.long)
+        return OracleEncoderOutput(self.enc.index_select(0, idx),
+                                   [(k.index_select(0, idx), v.index_select(0, idx)) for k, v in self.xkv])
+
     def __array__(self, dtype=None, copy=None):
         a = self.enc.numpy()
         return a.astype(dtype) if dtype is not None else a
@@ -71,6 +76,10 @@ class OracleWhisper:
     @property
     def n_mels(self) -> int:
         return self.dims.n_mels
+
+    @property
+    def vocab_size(self) -> int:
+        return self.dims.vocab
 
     @property
     def num_languages(self) -> int:

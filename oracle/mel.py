@@ -114,3 +114,6 @@ class OracleFeatureExtractor:
             self.n_samples = chunk_length * self.sampling_rate
             self.nb_max_frames = self.n_samples // self.hop_length
         return log_mel(waveform, self.feature_size, padding)
+
+    def batch(self, waveforms, padding=160, chunk_length=None):
+        return [self(w, padding, chunk_length) for w in waveforms]
