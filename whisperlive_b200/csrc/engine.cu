@@ -1,0 +1,1096 @@
+// libwlb200 engine: context, weights, encoder (K2-K7), decoder loop (K8-K13), alignment (K14) and
+// the C ABI declared in include/wlb200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wlb200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace wl;
+
+namespace wl {
+void gemm_prime();
+void attention_prime();
+long other_launch_count();
+}  // namespace wl
+
+static std::string g_init_error;
+
+struct EncLayer {
+  __half *w_qk, *w_v, *w_o, *w_fc1, *w_fc2;
+  float *b_qk, *b_v, *b_o, *b_fc1, *b_fc2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+struct DecLayer {
+  __half *w_qkv, *w_o, *w_qc, *w_kc, *w_vc, *w_oc, *w_fc1, *w_fc2;
+  float *b_qkv, *b_o, *b_qc, *b_vc, *b_oc, *b_fc1, *b_fc2;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+};
+
+struct wl_ctx {
+  wl_config cfg;
+  std::vector<int32_t> align_heads;
+  std::string err;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms[3] = {0, 0, 0};
+  int num_sms = 148;
+  int d, H, Le, Ld, n_mels, V, Vld, Bm, Km, Rm, NS;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  std::map<std::string, void*> dev;                 // raw uploaded tensors (fp16 for ndim>=2, f32 for 1-D)
+  std::map<std::string, std::vector<int64_t>> shape;
+  long launches = 0;
+
+  // weights
+  __half *w_conv1 = nullptr, *w_conv2 = nullptr, *emb = nullptr, *pos_dec = nullptr;
+  float *b_conv1, *b_conv2, *pos_enc, *lnp_g, *lnp_b, *lnf_g, *lnf_b;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  // mel
+  float *mel_window, *mel_twiddle, *mel_filt;
+  int* mel_range;
+  float* mel_pcm = nullptr;
+  float* mel_out = nullptr;
+  long *mel_off = nullptr, *mel_ooff = nullptr;
+  unsigned* mel_gmax = nullptr;
+  long mel_pcm_cap = 0, mel_out_cap = 0;
+  int mel_last_B = 0, mel_last_frames = 0;
+  // encoder workspaces
+  int EB, AB;
+  float* feat32;
+  __half *feat16, *conv1o, *xn, *qk, *vt, *probs16, *attn, *hbuf;
+  float *x, *scores;
+  int* enc_slots_dev;
+  // slot pool
+  __half* enc16;   // [NS][1500][d]
+  __half* ckv;     // [Ld][2][NS][H][1500][64]
+  std::vector<int> slot_free;
+  std::vector<char> slot_used;
+  // decoder workspaces
+  float *dx, *dqkv, *dqc, *logits;
+  __half *dxn, *datt, *dh, *kcache, *vcache;
+  long cache_row_stride, cache_layer_stride;
+  CrossAttnWorkspace xws;
+  float* align_probs = nullptr;   // [R][H][1500]
+  float* align_buf = nullptr;     // [B][nh][T_MAX][1500]
+  long align_buf_cap = 0;
+  int* align_heads_dev = nullptr;
+  DecodeState ds;
+  unsigned* suppress_mask;
+  // pinned host staging
+  int* h_int = nullptr;     // generic int staging
+  float* h_flt = nullptr;
+  size_t h_int_cap = 0, h_flt_cap = 0;
+  std::map<std::string, GraphEntry> graphs;
+};
+
+#define API_BEGIN(ctx)                                          \
+  if (!(ctx)) return WL_ERR_ARG;                                \
+  try {                                                         \
+    WL_CUDA(cudaSetDevice((ctx)->cfg.device));
+#define API_END(ctx)                                            \
+  }                                                             \
+  catch (const wl::Error& e) {                                  \
+    (ctx)->err = e.msg;                                         \
+    return e.code;                                              \
+  }                                                             \
+  catch (const std::exception& e) {                             \
+    (ctx)->err = e.what();                                      \
+    return WL_ERR_STATE;                                        \
+  }                                                             \
+  return WL_OK;
+
+template <class T>
+static T* dalloc(wl_ctx* c, size_t n, bool zero = true) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    char b[256];
+    snprintf(b, sizeof(b), "cudaMalloc of %.1f MB failed: %s", n * sizeof(T) / 1048576.0, cudaGetErrorString(e));
+    throw wl::Error{WL_ERR_NOMEM, b};
+  }
+  c->allocs.push_back(p);
+  if (zero) WL_CUDA(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return (T*)p;
+}
+
+static void ensure_host(wl_ctx* c, size_t n_int, size_t n_flt) {
+  if (n_int > c->h_int_cap) {
+    if (c->h_int) cudaFreeHost(c->h_int);
+    WL_CUDA(cudaMallocHost((void**)&c->h_int, n_int * sizeof(int)));
+    c->h_int_cap = n_int;
+  }
+  if (n_flt > c->h_flt_cap) {
+    if (c->h_flt) cudaFreeHost(c->h_flt);
+    WL_CUDA(cudaMallocHost((void**)&c->h_flt, n_flt * sizeof(float)));
+    c->h_flt_cap = n_flt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ init
+extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
+  if (!cfg || !out) return WL_ERR_ARG;
+  wl_ctx* c = new wl_ctx();
+  try {
+    WL_CHECK(cfg->abi_version == WL_ABI_VERSION, WL_ERR_ARG, "ABI version mismatch: header %d, caller %d", WL_ABI_VERSION,
+             cfg->abi_version);
+    c->cfg = *cfg;
+    c->align_heads.assign(cfg->align_heads, cfg->align_heads + 2 * cfg->n_align_heads);
+    c->cfg.align_heads = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    WL_CHECK(e == cudaSuccess && ndev > 0, WL_ERR_CUDA, "no CUDA device available (%s): libwlb200 has no CPU fallback",
+             cudaGetErrorString(e));
+    WL_CHECK(cfg->device >= 0 && cfg->device < ndev, WL_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    WL_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    WL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    WL_CHECK(prop.major == 10, WL_ERR_CUDA, "libwlb200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    c->num_sms = prop.multiProcessorCount;
+    c->d = cfg->d_model; c->H = cfg->n_heads; c->Le = cfg->enc_layers; c->Ld = cfg->dec_layers;
+    c->n_mels = cfg->n_mels; c->V = cfg->vocab; c->Vld = (cfg->vocab + 3) / 4 * 4;
+    c->Bm = cfg->max_streams; c->Km = cfg->max_beam; c->Rm = c->Bm * c->Km; c->NS = cfg->enc_slots;
+    WL_CHECK(c->d % 64 == 0 && c->H * 64 == c->d && c->d <= 1280, WL_ERR_ARG, "d_model %d / heads %d unsupported", c->d, c->H);
+    WL_CHECK(c->n_mels % 8 == 0 && c->n_mels <= 128, WL_ERR_ARG, "n_mels %d unsupported", c->n_mels);
+    WL_CHECK(c->Km >= 1 && c->Km <= MAX_ROWS_PER_STREAM, WL_ERR_ARG, "max_beam %d must be in [1,%d]", c->Km, MAX_ROWS_PER_STREAM);
+    WL_CHECK(c->Bm >= 1 && c->NS >= c->Bm, WL_ERR_ARG, "enc_slots %d must be >= max_streams %d", c->NS, c->Bm);
+    WL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    WL_CUDA(cudaEventCreate(&c->ev0));
+    WL_CUDA(cudaEventCreate(&c->ev1));
+    gemm_prime();
+    attention_prime();
+    c->enc.resize(c->Le);
+    c->dec.resize(c->Ld);
+    for (int i = c->NS - 1; i >= 0; --i) c->slot_free.push_back(i);
+    c->slot_used.assign(c->NS, 0);
+  } catch (const wl::Error& e) {
+    g_init_error = e.msg;
+    delete c;
+    return e.code;
+  }
+  *out = c;
+  return WL_OK;
+}
+
+extern "C" void wl_destroy(wl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->st);
+  for (auto& g : c->graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_int) cudaFreeHost(c->h_int);
+  if (c->h_flt) cudaFreeHost(c->h_flt);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
+extern "C" int64_t wl_kernel_launches(wl_ctx* c) { return c ? gemm_launch_count() + other_launch_count() : 0; }
+extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) { return (c && which >= 0 && which < 3) ? c->last_ms[which] : -1.f; }
+
+// ------------------------------------------------------------------------------------------ weights
+extern "C" int wl_load_tensor(wl_ctx* c, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  API_BEGIN(c)
+  WL_CHECK(name && data && shape && ndim >= 1 && ndim <= 3, WL_ERR_ARG, "wl_load_tensor: bad arguments");
+  WL_CHECK(!c->finalized, WL_ERR_STATE, "weights already finalized");
+  std::string nm(name);
+  size_t n = 1;
+  std::vector<int64_t> sh(shape, shape + ndim);
+  for (auto s : sh) n *= (size_t)s;
+  const bool as_f32 = ndim == 1 || nm == "model.encoder.embed_positions.weight" || nm == "mel_filters";
+  if (as_f32) {
+    float* p = dalloc<float>(c, n, false);
+    WL_CUDA(cudaMemcpy(p, data, n * sizeof(float), cudaMemcpyHostToDevice));
+    c->dev[nm] = p;
+  } else {
+    std::vector<__half> h(n);
+    if (ndim == 3) {
+      // conv weight [co][ci][k] -> [co][k][ci] so that conv-as-GEMM reads K = (k, ci) contiguously
+      const int64_t co = sh[0], ci = sh[1], kk = sh[2];
+      for (int64_t a = 0; a < co; ++a)
+        for (int64_t b = 0; b < ci; ++b)
+          for (int64_t k = 0; k < kk; ++k) h[(a * kk + k) * ci + b] = __float2half_rn(data[(a * ci + b) * kk + k]);
+    } else {
+      for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(data[i]);
+    }
+    __half* p = dalloc<__half>(c, n, false);
+    WL_CUDA(cudaMemcpy(p, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    c->dev[nm] = p;
+  }
+  c->shape[nm] = sh;
+  API_END(c)
+}
+
+static void* need(wl_ctx* c, const std::string& nm, std::initializer_list<int64_t> want) {
+  auto it = c->dev.find(nm);
+  WL_CHECK(it != c->dev.end(), WL_ERR_STATE, "missing weight tensor '%s'", nm.c_str());
+  const auto& sh = c->shape[nm];
+  std::vector<int64_t> w(want);
+  WL_CHECK(sh == w, WL_ERR_ARG, "weight '%s' has the wrong shape", nm.c_str());
+  return it->second;
+}
+static __half* concat_h(wl_ctx* c, std::vector<std::pair<__half*, size_t>> parts) {
+  size_t tot = 0;
+  for (auto& p : parts) tot += p.second;
+  __half* out = dalloc<__half>(c, tot, false);
+  size_t o = 0;
+  for (auto& p : parts) {
+    WL_CUDA(cudaMemcpy(out + o, p.first, p.second * sizeof(__half), cudaMemcpyDeviceToDevice));
+    o += p.second;
+  }
+  return out;
+}
+static float* concat_f(wl_ctx* c, std::vector<std::pair<float*, size_t>> parts) {
+  size_t tot = 0;
+  for (auto& p : parts) tot += p.second;
+  float* out = dalloc<float>(c, tot, true);
+  size_t o = 0;
+  for (auto& p : parts) {
+    if (p.first) WL_CUDA(cudaMemcpy(out + o, p.first, p.second * sizeof(float), cudaMemcpyDeviceToDevice));
+    o += p.second;
+  }
+  return out;
+}
+
+static void build_mel_tables(wl_ctx* c) {
+  std::vector<float> win(400), tw(800);
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < 400; ++i) {
+    win[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / 400.0));
+    tw[2 * i] = (float)cos(2.0 * PI * i / 400.0);
+    tw[2 * i + 1] = (float)sin(2.0 * PI * i / 400.0);
+  }
+  c->mel_window = dalloc<float>(c, 400);
+  c->mel_twiddle = dalloc<float>(c, 800);
+  WL_CUDA(cudaMemcpy(c->mel_window, win.data(), 400 * 4, cudaMemcpyHostToDevice));
+  WL_CUDA(cudaMemcpy(c->mel_twiddle, tw.data(), 800 * 4, cudaMemcpyHostToDevice));
+  c->mel_filt = (float*)need(c, "mel_filters", {c->n_mels, 201});
+  std::vector<float> f((size_t)c->n_mels * 201);
+  WL_CUDA(cudaMemcpy(f.data(), c->mel_filt, f.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int> rg(2 * c->n_mels);
+  for (int m = 0; m < c->n_mels; ++m) {
+    int lo = 201, hi = 0;
+    for (int k = 0; k < 201; ++k)
+      if (f[(size_t)m * 201 + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+    if (lo > hi) lo = hi = 0;
+    rg[2 * m] = lo; rg[2 * m + 1] = hi;
+  }
+  c->mel_range = dalloc<int>(c, rg.size());
+  WL_CUDA(cudaMemcpy(c->mel_range, rg.data(), rg.size() * 4, cudaMemcpyHostToDevice));
+  c->mel_gmax = dalloc<unsigned>(c, c->Bm);
+  c->mel_off = dalloc<long>(c, c->Bm + 1);
+  c->mel_ooff = dalloc<long>(c, c->Bm + 1);
+}
+
+extern "C" int wl_finalize_weights(wl_ctx* c) {
+  API_BEGIN(c)
+  WL_CHECK(!c->finalized, WL_ERR_STATE, "weights already finalized");
+  const int64_t d = c->d, ff = 4 * c->d, nm = c->n_mels, V = c->V;
+  const size_t dd = (size_t)d * d;
+  const std::string E = "model.encoder.", D = "model.decoder.";
+  c->w_conv1 = (__half*)need(c, E + "conv1.weight", {d, nm, 3});
+  c->b_conv1 = (float*)need(c, E + "conv1.bias", {d});
+  c->w_conv2 = (__half*)need(c, E + "conv2.weight", {d, d, 3});
+  c->b_conv2 = (float*)need(c, E + "conv2.bias", {d});
+  c->pos_enc = (float*)need(c, E + "embed_positions.weight", {S_ENC, d});
+  c->lnp_g = (float*)need(c, E + "layer_norm.weight", {d});
+  c->lnp_b = (float*)need(c, E + "layer_norm.bias", {d});
+  for (int l = 0; l < c->Le; ++l) {
+    const std::string p = E + "layers." + std::to_string(l) + ".";
+    EncLayer& L = c->enc[l];
+    L.w_qk = concat_h(c, {{(__half*)need(c, p + "self_attn.q_proj.weight", {d, d}), dd},
+                          {(__half*)need(c, p + "self_attn.k_proj.weight", {d, d}), dd}});
+    L.b_qk = concat_f(c, {{(float*)need(c, p + "self_attn.q_proj.bias", {d}), (size_t)d}, {nullptr, (size_t)d}});
+    L.w_v = (__half*)need(c, p + "self_attn.v_proj.weight", {d, d});
+    L.b_v = (float*)need(c, p + "self_attn.v_proj.bias", {d});
+    L.w_o = (__half*)need(c, p + "self_attn.out_proj.weight", {d, d});
+    L.b_o = (float*)need(c, p + "self_attn.out_proj.bias", {d});
+    L.ln1_g = (float*)need(c, p + "self_attn_layer_norm.weight", {d});
+    L.ln1_b = (float*)need(c, p + "self_attn_layer_norm.bias", {d});
+    L.w_fc1 = (__half*)need(c, p + "fc1.weight", {ff, d});
+    L.b_fc1 = (float*)need(c, p + "fc1.bias", {ff});
+    L.w_fc2 = (__half*)need(c, p + "fc2.weight", {d, ff});
+    L.b_fc2 = (float*)need(c, p + "fc2.bias", {d});
+    L.ln2_g = (float*)need(c, p + "final_layer_norm.weight", {d});
+    L.ln2_b = (float*)need(c, p + "final_layer_norm.bias", {d});
+  }
+  c->emb = (__half*)need(c, D + "embed_tokens.weight", {V, d});
+  c->pos_dec = (__half*)need(c, D + "embed_positions.weight", {T_MAX, d});
+  c->lnf_g = (float*)need(c, D + "layer_norm.weight", {d});
+  c->lnf_b = (float*)need(c, D + "layer_norm.bias", {d});
+  for (int l = 0; l < c->Ld; ++l) {
+    const std::string p = D + "layers." + std::to_string(l) + ".";
+    DecLayer& L = c->dec[l];
+    L.w_qkv = concat_h(c, {{(__half*)need(c, p + "self_attn.q_proj.weight", {d, d}), dd},
+                           {(__half*)need(c, p + "self_attn.k_proj.weight", {d, d}), dd},
+                           {(__half*)need(c, p + "self_attn.v_proj.weight", {d, d}), dd}});
+    L.b_qkv = concat_f(c, {{(float*)need(c, p + "self_attn.q_proj.bias", {d}), (size_t)d},
+                           {nullptr, (size_t)d},
+                           {(float*)need(c, p + "self_attn.v_proj.bias", {d}), (size_t)d}});
+    L.w_o = (__half*)need(c, p + "self_attn.out_proj.weight", {d, d});
+    L.b_o = (float*)need(c, p + "self_attn.out_proj.bias", {d});
+    L.ln1_g = (float*)need(c, p + "self_attn_layer_norm.weight", {d});
+    L.ln1_b = (float*)need(c, p + "self_attn_layer_norm.bias", {d});
+    L.w_qc = (__half*)need(c, p + "encoder_attn.q_proj.weight", {d, d});
+    L.b_qc = (float*)need(c, p + "encoder_attn.q_proj.bias", {d});
+    L.w_kc = (__half*)need(c, p + "encoder_attn.k_proj.weight", {d, d});
+    L.w_vc = (__half*)need(c, p + "encoder_attn.v_proj.weight", {d, d});
+    L.b_vc = (float*)need(c, p + "encoder_attn.v_proj.bias", {d});
+    L.w_oc = (__half*)need(c, p + "encoder_attn.out_proj.weight", {d, d});
+    L.b_oc = (float*)need(c, p + "encoder_attn.out_proj.bias", {d});
+    L.ln2_g = (float*)need(c, p + "encoder_attn_layer_norm.weight", {d});
+    L.ln2_b = (float*)need(c, p + "encoder_attn_layer_norm.bias", {d});
+    L.w_fc1 = (__half*)need(c, p + "fc1.weight", {ff, d});
+    L.b_fc1 = (float*)need(c, p + "fc1.bias", {ff});
+    L.w_fc2 = (__half*)need(c, p + "fc2.weight", {d, ff});
+    L.b_fc2 = (float*)need(c, p + "fc2.bias", {d});
+    L.ln3_g = (float*)need(c, p + "final_layer_norm.weight", {d});
+    L.ln3_b = (float*)need(c, p + "final_layer_norm.bias", {d});
+  }
+  build_mel_tables(c);
+
+  // ---- encoder workspaces (EB streams per pass, AB streams per attention sub-pass)
+  const int H = c->H;
+  c->EB = std::min(c->Bm, 8);
+  c->AB = std::min(c->EB, d >= 1024 ? 2 : 4);
+  const size_t M = (size_t)c->EB * S_ENC;
+  c->feat32 = dalloc<float>(c, (size_t)c->EB * nm * 3000);
+  c->feat16 = dalloc<__half>(c, (size_t)c->EB * 3002 * nm + 4096);
+  c->conv1o = dalloc<__half>(c, (size_t)c->EB * 3002 * d + 4096);
+  c->x = dalloc<float>(c, M * d);
+  c->xn = dalloc<__half>(c, M * d);
+  c->qk = dalloc<__half>(c, M * 2 * d);
+  c->vt = dalloc<__half>(c, (size_t)c->EB * d * S_PAD);
+  c->scores = dalloc<float>(c, (size_t)c->AB * H * S_ENC * S_PAD);
+  c->probs16 = dalloc<__half>(c, (size_t)c->AB * H * S_ENC * S_PAD);
+  c->attn = dalloc<__half>(c, M * d);
+  c->hbuf = dalloc<__half>(c, M * ff);
+  c->enc_slots_dev = dalloc<int>(c, c->Bm);
+  // ---- slot pool
+  c->enc16 = dalloc<__half>(c, (size_t)c->NS * S_ENC * d, false);
+  c->ckv = dalloc<__half>(c, (size_t)c->Ld * 2 * c->NS * S_ENC * d, false);
+  // ---- decoder workspaces
+  const size_t R = c->Rm, Rp = (R + 15) / 16 * 16;
+  c->dx = dalloc<float>(c, R * d);
+  c->dqkv = dalloc<float>(c, R * 3 * d);
+  c->dqc = dalloc<float>(c, R * d);
+  c->logits = dalloc<float>(c, R * c->Vld);
+  c->dxn = dalloc<__half>(c, Rp * d);
+  c->datt = dalloc<__half>(c, Rp * d);
+  c->dh = dalloc<__half>(c, Rp * ff);
+  c->cache_row_stride = (long)H * T_MAX * 64;
+  c->cache_layer_stride = (long)R * c->cache_row_stride;
+  c->kcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
+  c->vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
+  c->xws.part = dalloc<float>(c, (size_t)c->Bm * H * 12 * MAX_ROWS_PER_STREAM * 66);
+  c->xws.probs = nullptr;
+  c->suppress_mask = dalloc<unsigned>(c, (V + 31) / 32 + 1);
+  if (!c->align_heads.empty()) {
+    c->align_heads_dev = dalloc<int>(c, c->align_heads.size());
+    WL_CUDA(cudaMemcpy(c->align_heads_dev, c->align_heads.data(), c->align_heads.size() * 4, cudaMemcpyHostToDevice));
+  }
+  DecodeState& s = c->ds;
+  const size_t B = c->Bm;
+  s.tok_in = dalloc<int>(c, R); s.pos = dalloc<int>(c, R); s.active = dalloc<int>(c, R); s.cum = dalloc<float>(c, R);
+  s.gen_len = dalloc<int>(c, R); s.last_ts = dalloc<int>(c, R); s.row_done = dalloc<int>(c, R);
+  s.hist = dalloc<int>(c, R * T_MAX); s.src = dalloc<short>(c, R * T_MAX);
+  s.cand_val = dalloc<float>(c, R * MAX_CAND); s.cand_tok = dalloc<int>(c, R * MAX_CAND);
+  s.nospeech_row = dalloc<float>(c, R);
+  s.slot = dalloc<int>(c, B); s.prompt = dalloc<int>(c, B * T_MAX); s.prompt_len = dalloc<int>(c, B);
+  s.fed = dalloc<int>(c, B); s.sot_index = dalloc<int>(c, B); s.use_ts = dalloc<int>(c, B); s.n_new = dalloc<int>(c, B);
+  s.step = dalloc<int>(c, B); s.done = dalloc<int>(c, B); s.n_alive = dalloc<int>(c, B); s.no_speech = dalloc<float>(c, B);
+  s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
+  s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
+  s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
+  WL_CUDA(cudaDeviceSynchronize());
+  c->finalized = true;
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ K1 mel
+static void mel_run(wl_ctx* c) {
+  MelTables t{c->mel_window, c->mel_twiddle, c->mel_filt, c->mel_range, c->n_mels};
+  WL_CUDA(cudaEventRecord(c->ev0, c->st));
+  mel_forward(c->st, c->mel_pcm, c->mel_off, c->mel_out, c->mel_ooff, c->mel_gmax, t, c->mel_last_B, c->mel_last_frames);
+  WL_CUDA(cudaEventRecord(c->ev1, c->st));
+}
+
+extern "C" int wl_mel(wl_ctx* c, const float* pcm, const int64_t* offsets, int32_t B, float* out, const int64_t* out_offsets) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized, WL_ERR_STATE, "weights not finalized");
+  WL_CHECK(pcm && offsets && out && out_offsets && B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_mel: bad arguments (B=%d, max %d)", B, c->Bm);
+  const long total = offsets[B] - offsets[0];
+  int max_frames = 0;
+  std::vector<long> off(B + 1), ooff(B + 1);
+  for (int b = 0; b <= B; ++b) off[b] = offsets[b] - offsets[0];
+  for (int b = 0; b < B; ++b) {
+    const long n = off[b + 1] - off[b];
+    WL_CHECK(n > 0, WL_ERR_ARG, "wl_mel: empty waveform for stream %d", b);
+    const int T = (int)(n / 160) + 1;
+    max_frames = std::max(max_frames, T);
+    WL_CHECK(out_offsets[b + 1] - out_offsets[b] == (long)T * c->n_mels, WL_ERR_ARG, "wl_mel: out_offsets do not match frames");
+  }
+  for (int b = 0; b <= B; ++b) ooff[b] = out_offsets[b] - out_offsets[0];
+  if (total > c->mel_pcm_cap) {
+    c->mel_pcm = dalloc<float>(c, total + total / 4, false);
+    c->mel_pcm_cap = total + total / 4;
+  }
+  if (ooff[B] > c->mel_out_cap) {
+    c->mel_out = dalloc<float>(c, ooff[B] + ooff[B] / 4, false);
+    c->mel_out_cap = ooff[B] + ooff[B] / 4;
+  }
+  WL_CUDA(cudaMemcpyAsync(c->mel_pcm, pcm + offsets[0], total * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  WL_CUDA(cudaMemcpyAsync(c->mel_off, off.data(), (B + 1) * sizeof(long), cudaMemcpyHostToDevice, c->st));
+  WL_CUDA(cudaMemcpyAsync(c->mel_ooff, ooff.data(), (B + 1) * sizeof(long), cudaMemcpyHostToDevice, c->st));
+  c->mel_last_B = B;
+  c->mel_last_frames = max_frames;
+  mel_run(c);
+  WL_CUDA(cudaMemcpyAsync(out + out_offsets[0], c->mel_out, ooff[B] * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  WL_CUDA(cudaStreamSynchronize(c->st));
+  WL_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1));
+  API_END(c)
+}
+
+extern "C" int wl_mel_resident(wl_ctx* c) {
+  API_BEGIN(c)
+  WL_CHECK(c->mel_last_B > 0, WL_ERR_STATE, "wl_mel_resident: call wl_mel first");
+  mel_run(c);
+  WL_CUDA(cudaStreamSynchronize(c->st));
+  WL_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1));
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ K2-K7 encoder
+static GemmOperand opnd(const __half* p, long rows, long k, long ld, int n1 = 1, long s1 = 0, int n2 = 1, long s2 = 0) {
+  GemmOperand o;
+  o.ptr = p; o.rows = rows; o.k = k; o.ld = ld; o.n1 = n1; o.s1 = s1; o.n2 = n2; o.s2 = s2;
+  return o;
+}
+
+static void encoder_pass(wl_ctx* c, int nb, const int* slots_host) {
+  const int d = c->d, H = c->H, nm = c->n_mels, ff = 4 * c->d;
+  const long M = (long)nb * S_ENC;
+  cudaStream_t st = c->st;
+  prep_features(st, c->feat32, c->feat16, nb, nm);
+  {  // conv1 + GELU -> conv1o rows 1..3000 (rows 0 / 3001 stay zero)
+    GemmEpilogue e;
+    e.out = c->conv1o + d; e.out_f32 = 0; e.ldm = d; e.ldn = 1; e.ob1 = 3002L * d; e.bias = c->b_conv1; e.gelu = 1;
+    gemm_tn(st, opnd(c->feat16, 3000, 3 * nm, nm, nb, 3002L * nm), opnd(c->w_conv1, d, 3 * nm, 3 * nm), 3000, d, 3 * nm, e);
+  }
+  {  // conv2 (stride 2) + GELU + positional table -> residual stream x (f32)
+    GemmEpilogue e;
+    e.out = c->x; e.out_f32 = 1; e.ldm = d; e.ldn = 1; e.ob1 = (long)S_ENC * d; e.bias = c->b_conv2; e.gelu = 1;
+    e.resid = c->pos_enc; e.rldm = d; e.rldn = 1; e.rb1 = 0;
+    gemm_tn(st, opnd(c->conv1o, S_ENC, 3 * d, 2 * d, nb, 3002L * d), opnd(c->w_conv2, d, 3 * d, 3 * d), S_ENC, d, 3 * d, e);
+  }
+  for (int l = 0; l < c->Le; ++l) {
+    const EncLayer& L = c->enc[l];
+    layernorm_rows(st, c->x, L.ln1_g, L.ln1_b, c->xn, nullptr, M, d);
+    {
+      GemmEpilogue e;
+      e.out = c->qk; e.ldm = 2 * d; e.bias = L.b_qk;
+      gemm_tn(st, opnd(c->xn, M, d, d), opnd(L.w_qk, 2 * d, d, d), (int)M, 2 * d, d, e);
+    }
+    {  // V^T[b] = Wv * xn[b]^T  (swap-AB) so that P*V reads V K-major
+      GemmEpilogue e;
+      e.out = c->vt; e.ldm = S_PAD; e.ldn = 1; e.ob1 = (long)d * S_PAD; e.bias = L.b_v; e.bias_on_m = 1;
+      gemm_tn(st, opnd(L.w_v, d, d, d), opnd(c->xn, S_ENC, d, d, nb, (long)S_ENC * d), d, S_ENC, d, e);
+    }
+    for (int b0 = 0; b0 < nb; b0 += c->AB) {
+      const int ab = std::min(c->AB, nb - b0);
+      const __half* qb = c->qk + (long)b0 * S_ENC * 2 * d;
+      {
+        GemmEpilogue e;
+        e.out = c->scores; e.out_f32 = 1; e.ldm = S_PAD; e.ob1 = (long)S_ENC * S_PAD; e.ob2 = (long)H * S_ENC * S_PAD;
+        gemm_tn(st, opnd(qb, S_ENC, 64, 2 * d, H, 64, ab, (long)S_ENC * 2 * d),
+                opnd(qb + d, S_ENC, 64, 2 * d, H, 64, ab, (long)S_ENC * 2 * d), S_ENC, S_ENC, 64, e);
+      }
+      softmax_rows(st, c->scores, c->probs16, (long)ab * H * S_ENC, S_ENC, S_PAD, S_PAD, 0.125f);
+      {
+        GemmEpilogue e;
+        e.out = c->attn + (long)b0 * S_ENC * d; e.ldm = d; e.ob1 = 64; e.ob2 = (long)S_ENC * d;
+        gemm_tn(st, opnd(c->probs16, S_ENC, S_PAD, S_PAD, H, (long)S_ENC * S_PAD, ab, (long)H * S_ENC * S_PAD),
+                opnd(c->vt + (long)b0 * d * S_PAD, 64, S_PAD, S_PAD, H, 64L * S_PAD, ab, (long)d * S_PAD), S_ENC, 64, S_PAD, e);
+      }
+    }
+    {
+      GemmEpilogue e;
+      e.out = c->x; e.out_f32 = 1; e.ldm = d; e.bias = L.b_o; e.resid = c->x; e.rldm = d;
+      gemm_tn(st, opnd(c->attn, M, d, d), opnd(L.w_o, d, d, d), (int)M, d, d, e);
+    }
+    layernorm_rows(st, c->x, L.ln2_g, L.ln2_b, c->xn, nullptr, M, d);
+    {
+      GemmEpilogue e;
+      e.out = c->hbuf; e.ldm = ff; e.bias = L.b_fc1; e.gelu = 1;
+      gemm_tn(st, opnd(c->xn, M, d, d), opnd(L.w_fc1, ff, d, d), (int)M, ff, d, e);
+    }
+    {
+      GemmEpilogue e;
+      e.out = c->x; e.out_f32 = 1; e.ldm = d; e.bias = L.b_fc2; e.resid = c->x; e.rldm = d;
+      gemm_tn(st, opnd(c->hbuf, M, ff, ff), opnd(L.w_fc2, d, ff, ff), (int)M, d, ff, e);
+    }
+  }
+  layernorm_rows(st, c->x, c->lnp_g, c->lnp_b, c->xn, nullptr, M, d);
+  for (int b = 0; b < nb; ++b)
+    WL_CUDA(cudaMemcpyAsync(c->enc16 + (long)slots_host[b] * S_ENC * d, c->xn + (long)b * S_ENC * d,
+                            (size_t)S_ENC * d * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  // K7: cross-attention K/V of every decoder layer straight into the slot pool ([slot][H][1500][64])
+  const long slot_sz = (long)S_ENC * d;
+  for (int l = 0; l < c->Ld; ++l) {
+    const DecLayer& L = c->dec[l];
+    GemmEpilogue e;
+    e.mode = GEMM_HEADSPLIT; e.hs_S = S_ENC; e.hs_H = H; e.hs_slot_stride = slot_sz; e.hs_slots = c->enc_slots_dev;
+    e.out = c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz;
+    gemm_tn(st, opnd(c->xn, M, d, d), opnd(L.w_kc, d, d, d), (int)M, d, d, e);
+    e.out = c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz;
+    e.bias = L.b_vc;
+    gemm_tn(st, opnd(c->xn, M, d, d), opnd(L.w_vc, d, d, d), (int)M, d, d, e);
+  }
+}
+
+static void encode_impl(wl_ctx* c, const float* features_host, int B, const int* slots, bool resident) {
+  const size_t per = (size_t)c->n_mels * 3000;
+  float ms_total = 0.f;
+  for (int b0 = 0; b0 < B; b0 += c->EB) {
+    const int nb = std::min(c->EB, B - b0);
+    if (!resident)
+      WL_CUDA(cudaMemcpyAsync(c->feat32, features_host + b0 * per, nb * per * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    WL_CUDA(cudaMemcpyAsync(c->enc_slots_dev, slots + b0, nb * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    WL_CUDA(cudaEventRecord(c->ev0, c->st));
+    encoder_pass(c, nb, slots + b0);
+    WL_CUDA(cudaEventRecord(c->ev1, c->st));
+    WL_CUDA(cudaStreamSynchronize(c->st));
+    float ms;
+    WL_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    ms_total += ms;
+  }
+  c->last_ms[1] = ms_total;
+}
+
+extern "C" int wl_encode(wl_ctx* c, const float* features, int32_t B, int32_t* slots_out) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized, WL_ERR_STATE, "weights not finalized");
+  WL_CHECK(features && slots_out && B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_encode: bad arguments (B=%d, max %d)", B, c->Bm);
+  WL_CHECK((int)c->slot_free.size() >= B, WL_ERR_NOMEM, "wl_encode: %d encoder slots requested, %d free", B, (int)c->slot_free.size());
+  for (int b = 0; b < B; ++b) {
+    slots_out[b] = c->slot_free.back();
+    c->slot_free.pop_back();
+    c->slot_used[slots_out[b]] = 1;
+  }
+  try {
+    encode_impl(c, features, B, slots_out, false);
+  } catch (...) {
+    for (int b = 0; b < B; ++b) { c->slot_used[slots_out[b]] = 0; c->slot_free.push_back(slots_out[b]); }
+    throw;
+  }
+  API_END(c)
+}
+
+extern "C" int wl_encode_resident(wl_ctx* c, int32_t B, const int32_t* slots) {
+  API_BEGIN(c)
+  WL_CHECK(B >= 1 && B <= c->EB, WL_ERR_ARG, "wl_encode_resident: B must be <= %d", c->EB);
+  for (int b = 0; b < B; ++b) WL_CHECK(slots[b] >= 0 && slots[b] < c->NS && c->slot_used[slots[b]], WL_ERR_ARG, "bad slot");
+  encode_impl(c, nullptr, B, slots, true);
+  API_END(c)
+}
+
+extern "C" int wl_slots_release(wl_ctx* c, const int32_t* slots, int32_t n) {
+  API_BEGIN(c)
+  for (int i = 0; i < n; ++i) {
+    WL_CHECK(slots[i] >= 0 && slots[i] < c->NS && c->slot_used[slots[i]], WL_ERR_ARG, "wl_slots_release: slot %d is not in use", slots[i]);
+    c->slot_used[slots[i]] = 0;
+    c->slot_free.push_back(slots[i]);
+  }
+  API_END(c)
+}
+extern "C" int wl_slots_free_count(wl_ctx* c) { return c ? (int)c->slot_free.size() : -1; }
+
+extern "C" int wl_encoder_output(wl_ctx* c, int32_t slot, float* out) {
+  API_BEGIN(c)
+  WL_CHECK(out && slot >= 0 && slot < c->NS && c->slot_used[slot], WL_ERR_ARG, "wl_encoder_output: bad slot %d", slot);
+  const size_t n = (size_t)S_ENC * c->d;
+  std::vector<__half> h(n);
+  WL_CUDA(cudaMemcpy(h.data(), c->enc16 + (long)slot * n, n * sizeof(__half), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) out[i] = __half2float(h[i]);
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ decoder step
+namespace wl {
+void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* probs, float* buf, const int* heads, int n_heads,
+                        int layer, int B, int rows_per_stream, int H);
+}
+
+static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const VocabIds& vi, int nsplit, bool align_mode) {
+  const int d = c->d, H = c->H, ff = 4 * c->d, R = B * Kr;
+  cudaStream_t st = c->st;
+  const DecodeState& s = c->ds;
+  const long slot_sz = (long)S_ENC * d;
+  decoder_embed(st, s, c->emb, c->pos_dec, c->dx, R, d);
+  auto swap_gemm = [&](const __half* W, int n_out, int K, const __half* X, GemmEpilogue e) {
+    e.ldm = 1;
+    e.bias_on_m = 1;
+    gemm_tn(st, opnd(W, n_out, K, K), opnd(X, R, K, K), n_out, R, K, e);
+  };
+  for (int l = 0; l < c->Ld; ++l) {
+    const DecLayer& L = c->dec[l];
+    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d);
+    {
+      GemmEpilogue e;
+      e.out = c->dqkv; e.out_f32 = 1; e.ldn = 3 * d; e.bias = L.b_qkv;
+      swap_gemm(L.w_qkv, 3 * d, d, c->dxn, e);
+    }
+    decoder_self_attn(st, s, c->dqkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
+                      c->cache_row_stride, c->datt, R, H, d);
+    {
+      GemmEpilogue e;
+      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_o; e.resid = c->dx; e.rldm = 1; e.rldn = d;
+      swap_gemm(L.w_o, d, d, c->datt, e);
+    }
+    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d);
+    {
+      GemmEpilogue e;
+      e.out = c->dqc; e.out_f32 = 1; e.ldn = d; e.bias = L.b_qc;
+      swap_gemm(L.w_qc, d, d, c->dxn, e);
+    }
+    CrossAttnWorkspace ws = c->xws;
+    ws.probs = align_mode ? c->align_probs : nullptr;
+    decoder_cross_attn(st, s, c->dqc, c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz, c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz,
+                       slot_sz, ws, c->datt, B, Kr, H, d, nsplit);
+    if (align_mode)
+      gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
+    {
+      GemmEpilogue e;
+      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_oc; e.resid = c->dx; e.rldm = 1; e.rldn = d;
+      swap_gemm(L.w_oc, d, d, c->datt, e);
+    }
+    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d);
+    {
+      GemmEpilogue e;
+      e.out = c->dh; e.out_f32 = 0; e.ldn = ff; e.bias = L.b_fc1; e.gelu = 1;
+      swap_gemm(L.w_fc1, ff, d, c->dxn, e);
+    }
+    {
+      GemmEpilogue e;
+      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_fc2; e.resid = c->dx; e.rldm = 1; e.rldn = d;
+      swap_gemm(L.w_fc2, d, ff, c->dh, e);
+    }
+  }
+  layernorm_rows(st, c->dx, c->lnf_g, c->lnf_b, c->dxn, nullptr, R, d);
+  {
+    GemmEpilogue e;
+    e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;
+    e.ldm = 1;
+    gemm_tn(st, opnd(c->emb, c->V, d, d), opnd(c->dxn, R, d, d), c->V, R, d, e);
+  }
+  search_rows(st, s, c->logits, so, vi, R);
+  search_streams(st, s, so, vi, B);
+}
+
+static VocabIds vocab_ids(wl_ctx* c) {
+  VocabIds v;
+  v.vocab = c->V; v.vocab_ld = c->Vld; v.eot = c->cfg.eot; v.sot = c->cfg.sot; v.no_speech = c->cfg.no_speech;
+  v.no_timestamps = c->cfg.no_timestamps; v.ts_begin = c->cfg.timestamp_begin; v.blank = c->cfg.blank;
+  return v;
+}
+
+// upload prompts & per-stream metadata; returns max steps
+static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t* prompts, const int32_t* off, int max_length,
+                          bool forced) {
+  ensure_host(c, (size_t)B * (T_MAX + 8), 16);
+  int* hp = c->h_int;                      // [B][T_MAX]
+  int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len  (6 x B)
+  int max_steps = 0;
+  for (int b = 0; b < B; ++b) {
+    const int P = off[b + 1] - off[b];
+    WL_CHECK(P >= 1 && P <= T_MAX, WL_ERR_ARG, "stream %d: prompt length %d out of range", b, P);
+    WL_CHECK(slots[b] >= 0 && slots[b] < c->NS && c->slot_used[slots[b]], WL_ERR_ARG, "stream %d: bad encoder slot %d", b, slots[b]);
+    int sot = -1;
+    for (int i = 0; i < P; ++i) {
+      const int t = prompts[off[b] + i];
+      WL_CHECK(t >= 0 && t < c->V, WL_ERR_ARG, "stream %d: token id %d out of range", b, t);
+      hp[(size_t)b * T_MAX + i] = t;
+      if (t == c->cfg.sot && sot < 0) sot = i;
+    }
+    int n_new = 0;
+    if (!forced) {
+      n_new = std::min(max_length / 2, max_length - P);
+      WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, max_length);
+      max_steps = std::max(max_steps, P - 1 + n_new);
+    } else {
+      max_steps = std::max(max_steps, P);
+    }
+    meta[0 * B + b] = slots[b];
+    meta[1 * B + b] = P;
+    meta[2 * B + b] = sot;
+    meta[3 * B + b] = prompts[off[b] + P - 1] != c->cfg.no_timestamps;
+    meta[4 * B + b] = n_new;
+    meta[5 * B + b] = forced ? P : 0;
+  }
+  const DecodeState& s = c->ds;
+  cudaStream_t st = c->st;
+  WL_CUDA(cudaMemcpyAsync(s.prompt, hp, (size_t)B * T_MAX * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.slot, meta + 0 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.prompt_len, meta + 1 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.sot_index, meta + 2 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.use_ts, meta + 3 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.n_new, meta + 4 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.force_len, meta + 5 * B, B * 4, cudaMemcpyHostToDevice, st));
+  return max_steps;
+}
+
+extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int32_t* prompts, const int32_t* prompt_off,
+                           const wl_gen_opts* o, int32_t* out_ids, int32_t* out_len, float* out_score, float* out_no_speech,
+                           int32_t* out_steps) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized, WL_ERR_STATE, "weights not finalized");
+  WL_CHECK(slots && prompts && prompt_off && o && out_ids && out_len && out_score, WL_ERR_ARG, "wl_generate: null argument");
+  WL_CHECK(B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_generate: B=%d exceeds max_streams=%d", B, c->Bm);
+  WL_CHECK(o->beam_size >= 1 && o->num_hypotheses >= 1, WL_ERR_ARG, "wl_generate: beam_size / num_hypotheses must be >= 1");
+  const int K = o->beam_size;
+  const int Kr = K > 1 ? K : o->num_hypotheses;
+  WL_CHECK(Kr <= c->Km, WL_ERR_ARG, "wl_generate: %d rows per stream exceed max_beam=%d", Kr, c->Km);
+  WL_CHECK(K == 1 || o->num_hypotheses <= MAX_HYPS, WL_ERR_ARG, "too many hypotheses");
+  WL_CHECK(o->sampling_topk == 0 || o->sampling_topk == 1, WL_ERR_ARG, "sampling_topk must be 0 (full) or 1 (arg-max)");
+  WL_CHECK(o->max_length >= 2 && o->max_length <= T_MAX, WL_ERR_ARG, "max_length %d out of range", o->max_length);
+  const int R = B * Kr;
+  SearchOpts so;
+  so.beam = K; so.rows_per_stream = Kr;
+  so.max_cand = std::max(1, std::min(MAX_HYPS, (int)lroundf(K * o->patience)));
+  so.suppress_blank = o->suppress_blank; so.max_initial_ts = o->max_initial_timestamp_index;
+  so.sampling = (K == 1 && o->sampling_topk == 0 && o->sampling_temperature > 0.f) ? 1 : 0;
+  so.temperature = o->sampling_temperature; so.seed = o->seed; so.suppress_mask = c->suppress_mask;
+  const VocabIds vi = vocab_ids(c);
+  cudaStream_t st = c->st;
+  // suppress bitmask
+  const int nwords = (c->V + 31) / 32 + 1;
+  std::vector<unsigned> mask(nwords, 0u);
+  for (int i = 0; i < o->n_suppress; ++i) {
+    const int t = o->suppress_tokens[i];
+    if (t >= 0 && t < c->V) mask[t >> 5] |= 1u << (t & 31);
+  }
+  const int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false);
+  WL_CUDA(cudaMemcpyAsync(c->suppress_mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaEventRecord(c->ev0, st));
+  decode_init(st, c->ds, so, vi, B, R);
+  const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms);
+
+  cudaGraphExec_t exec = nullptr;
+  if (o->use_cuda_graph) {
+    char key[160];
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x/%u", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
+             so.sampling, *(const unsigned*)&so.temperature, so.seed);
+    GraphEntry& ge = c->graphs[key];
+    if (!ge.exec) {
+      cudaGraph_t g;
+      WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(c, B, Kr, so, vi, nsplit, false);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        throw;
+      }
+      WL_CUDA(cudaStreamEndCapture(st, &g));
+      WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
+      cudaGraphDestroy(g);
+    }
+    exec = ge.exec;
+  }
+  ensure_host(c, (size_t)B * (T_MAX + 8) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
+  int* h_done = c->h_int;  // reuse (prompts are already on the device: the copies above are stream-ordered)
+  WL_CUDA(cudaStreamSynchronize(st));
+  int ran = 0;
+  const int check_every = 4;
+  while (ran < max_steps) {
+    const int n = std::min(check_every, max_steps - ran);
+    for (int i = 0; i < n; ++i) {
+      if (exec) WL_CUDA(cudaGraphLaunch(exec, st));
+      else decode_step(c, B, Kr, so, vi, nsplit, false);
+    }
+    ran += n;
+    WL_CUDA(cudaMemcpyAsync(h_done, c->ds.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WL_CUDA(cudaStreamSynchronize(st));
+    if (*h_done >= B) break;
+  }
+  WL_CUDA(cudaEventRecord(c->ev1, st));
+  // results
+  const DecodeState& s = c->ds;
+  int* h_cnt = c->h_int;
+  int* h_len = h_cnt + B;
+  int* h_steps = h_len + (size_t)B * MAX_HYPS;
+  int* h_tok = h_steps + B;
+  float* h_cum = c->h_flt;
+  float* h_ns = h_cum + (size_t)B * MAX_HYPS;
+  WL_CUDA(cudaMemcpyAsync(h_cnt, s.hyp_count, B * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_len, s.hyp_len, (size_t)B * MAX_HYPS * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_steps, s.steps_run, B * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_tok, s.hyp_tok, (size_t)B * MAX_HYPS * T_MAX * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_cum, s.hyp_cum, (size_t)B * MAX_HYPS * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_ns, s.no_speech, B * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaStreamSynchronize(st));
+  WL_CUDA(cudaEventElapsedTime(&c->last_ms[2], c->ev0, c->ev1));
+  const int NH = o->num_hypotheses;
+  for (int b = 0; b < B; ++b) {
+    const int cnt = std::min(h_cnt[b], MAX_HYPS);
+    std::vector<int> order(cnt);
+    std::vector<float> score(cnt);
+    for (int i = 0; i < cnt; ++i) {
+      order[i] = i;
+      const int len = h_len[b * MAX_HYPS + i];
+      score[i] = o->length_penalty == 0.f ? h_cum[b * MAX_HYPS + i]
+                                          : h_cum[b * MAX_HYPS + i] / powf((float)std::max(len, 1), o->length_penalty);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return score[a] > score[bb]; });
+    for (int hh = 0; hh < NH; ++hh) {
+      int* dst = out_ids + ((size_t)b * NH + hh) * T_MAX;
+      if (hh < cnt) {
+        const int i = order[hh];
+        const int len = h_len[b * MAX_HYPS + i];
+        memcpy(dst, h_tok + ((size_t)b * MAX_HYPS + i) * T_MAX, len * sizeof(int));
+        out_len[b * NH + hh] = len;
+        out_score[b * NH + hh] = score[i];
+      } else {
+        out_len[b * NH + hh] = -1;
+        out_score[b * NH + hh] = 0.f;
+      }
+    }
+    if (out_no_speech) out_no_speech[b] = h_ns[b];
+    if (out_steps) out_steps[b] = h_steps[b];
+  }
+  API_END(c)
+}
+
+// teacher-forced driver shared by wl_decode_logits / wl_detect_language / wl_align
+static void forced_run(wl_ctx* c, const int32_t* slots, int B, const int32_t* tokens, const int32_t* off, bool align_mode,
+                       float* logits_out_dev /* [sumT][V] or null */, const std::vector<long>& row_base) {
+  SearchOpts so;
+  memset(&so, 0, sizeof(so));
+  so.beam = 1; so.rows_per_stream = 1; so.max_cand = 1; so.suppress_mask = c->suppress_mask;
+  const VocabIds vi = vocab_ids(c);
+  cudaStream_t st = c->st;
+  const int max_steps = upload_streams(c, slots, B, tokens, off, T_MAX, true);
+  decode_init(st, c->ds, so, vi, B, B);
+  const int nsplit = align_mode ? 1 : cross_attn_pick_nsplit(B, c->H, c->num_sms);
+  for (int i = 0; i < max_steps; ++i) {
+    decode_step(c, B, 1, so, vi, nsplit, align_mode);
+    if (logits_out_dev)
+      for (int b = 0; b < B; ++b)
+        if (i < off[b + 1] - off[b])
+          WL_CUDA(cudaMemcpyAsync(logits_out_dev + (row_base[b] + i) * c->V, c->logits + (long)b * c->Vld, (size_t)c->V * 4,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  WL_CUDA(cudaStreamSynchronize(st));
+}
+
+extern "C" int wl_decode_logits(wl_ctx* c, const int32_t* slots, int32_t B, const int32_t* tokens, const int32_t* tok_off,
+                                float* logits_out) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized && slots && tokens && tok_off && logits_out && B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_decode_logits: bad arguments");
+  std::vector<long> base(B);
+  long tot = 0;
+  for (int b = 0; b < B; ++b) { base[b] = tot; tot += tok_off[b + 1] - tok_off[b]; }
+  float* dev = nullptr;
+  WL_CUDA(cudaMalloc((void**)&dev, (size_t)tot * c->V * 4));
+  try {
+    forced_run(c, slots, B, tokens, tok_off, false, dev, base);
+    WL_CUDA(cudaMemcpy(logits_out, dev, (size_t)tot * c->V * 4, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    cudaFree(dev);
+    throw;
+  }
+  cudaFree(dev);
+  API_END(c)
+}
+
+extern "C" int wl_detect_language(wl_ctx* c, const int32_t* slots, int32_t B, float* probs) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized && slots && probs && B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_detect_language: bad arguments");
+  WL_CHECK(c->cfg.n_lang > 0, WL_ERR_STATE, "detect_language can only be called on multilingual models");
+  std::vector<int32_t> toks(B, c->cfg.sot), off(B + 1);
+  std::vector<long> base(B);
+  for (int b = 0; b <= B; ++b) off[b] = b;
+  forced_run(c, slots, B, toks.data(), off.data(), false, nullptr, base);
+  const int nl = c->cfg.n_lang;
+  std::vector<float> lg((size_t)B * nl);
+  for (int b = 0; b < B; ++b)
+    WL_CUDA(cudaMemcpy(lg.data() + (size_t)b * nl, c->logits + (long)b * c->Vld + c->cfg.lang_begin, nl * 4, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < B; ++b) {
+    float mx = -INFINITY;
+    for (int i = 0; i < nl; ++i) mx = std::max(mx, lg[(size_t)b * nl + i]);
+    double sum = 0;
+    for (int i = 0; i < nl; ++i) sum += exp((double)lg[(size_t)b * nl + i] - mx);
+    for (int i = 0; i < nl; ++i) probs[(size_t)b * nl + i] = (float)(exp((double)lg[(size_t)b * nl + i] - mx) / sum);
+  }
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ K14 align
+static void median_filter_row(const float* in, float* out, int n, int width) {
+  const int pad = width / 2;
+  if (pad == 0 || n <= pad) { memcpy(out, in, n * sizeof(float)); return; }
+  std::vector<float> w(width);
+  for (int i = 0; i < n; ++i) {
+    for (int k = -pad; k <= pad; ++k) {
+      int j = i + k;
+      if (j < 0) j = -j;
+      if (j >= n) j = 2 * (n - 1) - j;
+      w[k + pad] = in[j];
+    }
+    std::nth_element(w.begin(), w.begin() + pad, w.end());
+    out[i] = w[pad];
+  }
+}
+
+static void dtw_path(const std::vector<float>& cost, int n, int m, std::vector<std::pair<int, int>>& path) {
+  std::vector<float> acc((size_t)(n + 1) * (m + 1), INFINITY);
+  std::vector<signed char> mv((size_t)(n + 1) * (m + 1), -1);
+  auto A = [&](int i, int j) -> float& { return acc[(size_t)i * (m + 1) + j]; };
+  auto Mv = [&](int i, int j) -> signed char& { return mv[(size_t)i * (m + 1) + j]; };
+  A(0, 0) = 0.f;
+  for (int j = 1; j <= m; ++j)
+    for (int i = 1; i <= n; ++i) {
+      const float c0 = A(i - 1, j - 1), c1 = A(i - 1, j), c2 = A(i, j - 1);
+      float cc; signed char t;
+      if (c0 < c1 && c0 < c2) { cc = c0; t = 0; }
+      else if (c1 < c0 && c1 < c2) { cc = c1; t = 1; }
+      else { cc = c2; t = 2; }
+      A(i, j) = cost[(size_t)(i - 1) * m + (j - 1)] + cc;
+      Mv(i, j) = t;
+    }
+  for (int j = 0; j <= m; ++j) Mv(0, j) = 2;
+  for (int i = 0; i <= n; ++i) Mv(i, 0) = 1;
+  int i = n, j = m;
+  path.clear();
+  while (i > 0 || j > 0) {
+    path.emplace_back(i - 1, j - 1);
+    const signed char t = Mv(i, j);
+    if (t == 0) { --i; --j; }
+    else if (t == 1) --i;
+    else --j;
+  }
+  std::reverse(path.begin(), path.end());
+}
+
+extern "C" int wl_align(wl_ctx* c, const int32_t* slots, int32_t B, const int32_t* start_seq, int32_t n_start, const int32_t* text,
+                        const int32_t* text_off, const int32_t* num_frames, int32_t median_width, int32_t* pairs_out,
+                        int32_t cap_pairs, int32_t* pair_off, float* tok_probs) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized && slots && start_seq && text && text_off && num_frames && pairs_out && pair_off && tok_probs, WL_ERR_ARG,
+           "wl_align: null argument");
+  WL_CHECK(B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_align: B=%d exceeds max_streams", B);
+  const int nh = (int)c->align_heads.size() / 2;
+  WL_CHECK(nh > 0, WL_ERR_STATE, "wl_align: no alignment heads configured");
+  std::vector<int32_t> toks, off(B + 1);
+  std::vector<long> base(B, 0);
+  int maxT = 0;
+  off[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < n_start; ++i) toks.push_back(start_seq[i]);
+    toks.push_back(c->cfg.no_timestamps);
+    for (int i = text_off[b]; i < text_off[b + 1]; ++i) toks.push_back(text[i]);
+    toks.push_back(c->cfg.eot);
+    off[b + 1] = (int)toks.size();
+    maxT = std::max(maxT, off[b + 1] - off[b]);
+  }
+  WL_CHECK(maxT <= T_MAX, WL_ERR_ARG, "wl_align: sequence of %d tokens exceeds %d", maxT, T_MAX);
+  if (!c->align_probs) c->align_probs = dalloc<float>(c, (size_t)c->Rm * c->H * S_ENC);
+  const long need_buf = (long)B * nh * T_MAX * S_ENC;
+  if (need_buf > c->align_buf_cap) {
+    c->align_buf = dalloc<float>(c, need_buf, false);
+    c->align_buf_cap = need_buf;
+  }
+  forced_run(c, slots, B, toks.data(), off.data(), true, nullptr, base);
+  std::vector<float> fprob((size_t)B * T_MAX);
+  WL_CUDA(cudaMemcpy(fprob.data(), c->ds.force_prob, fprob.size() * 4, cudaMemcpyDeviceToHost));
+  int np_total = 0;
+  pair_off[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    const int T = off[b + 1] - off[b], nt = text_off[b + 1] - text_off[b];
+    const int nf = std::max(1, std::min(num_frames[b] / 2, (int)S_ENC));
+    for (int i = 0; i < nt; ++i) tok_probs[text_off[b] + i] = fprob[(size_t)b * T_MAX + n_start + i];
+    // W[h][t][f]: standardise over tokens, median filter over time, mean over heads
+    std::vector<float> W((size_t)nh * T * nf), row(S_ENC), tmp(nf), outr(nf);
+    for (int h = 0; h < nh; ++h)
+      for (int t = 0; t < T; ++t) {
+        WL_CUDA(cudaMemcpy(row.data(), c->align_buf + (((long)b * nh + h) * T_MAX + t) * S_ENC, nf * 4, cudaMemcpyDeviceToHost));
+        memcpy(&W[((size_t)h * T + t) * nf], row.data(), nf * 4);
+      }
+    std::vector<float> mat((size_t)T * nf, 0.f);
+    for (int h = 0; h < nh; ++h) {
+      for (int f = 0; f < nf; ++f) {
+        double mean = 0, var = 0;
+        for (int t = 0; t < T; ++t) mean += W[((size_t)h * T + t) * nf + f];
+        mean /= T;
+        for (int t = 0; t < T; ++t) { const double dlt = W[((size_t)h * T + t) * nf + f] - mean; var += dlt * dlt; }
+        const float sd = (float)sqrt(var / T);
+        for (int t = 0; t < T; ++t) W[((size_t)h * T + t) * nf + f] = (float)((W[((size_t)h * T + t) * nf + f] - mean) / sd);
+      }
+      for (int t = 0; t < T; ++t) {
+        median_filter_row(&W[((size_t)h * T + t) * nf], outr.data(), nf, median_width);
+        for (int f = 0; f < nf; ++f) mat[(size_t)t * nf + f] += outr[f] / nh;
+      }
+    }
+    const int n_rows = T - 1 - n_start;  // rows [n_start, T-1)
+    std::vector<float> cost((size_t)n_rows * nf);
+    for (int t = 0; t < n_rows; ++t)
+      for (int f = 0; f < nf; ++f) cost[(size_t)t * nf + f] = -mat[(size_t)(t + n_start) * nf + f];
+    std::vector<std::pair<int, int>> path;
+    dtw_path(cost, n_rows, nf, path);
+    WL_CHECK(np_total + (int)path.size() <= cap_pairs, WL_ERR_ARG, "wl_align: pairs_out capacity %d too small", cap_pairs);
+    for (auto& p : path) {
+      pairs_out[2 * np_total] = p.first;
+      pairs_out[2 * np_total + 1] = p.second;
+      ++np_total;
+    }
+    pair_off[b + 1] = np_total;
+  }
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ test hook
+extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_f16, const float* bias, float* cc, int32_t M,
+                            int32_t N, int32_t K, int32_t batch, int32_t transposed_store, int32_t gelu, int32_t use_simt) {
+  API_BEGIN(c)
+  __half *da = nullptr, *db = nullptr;
+  float *dbias = nullptr, *dc = nullptr;
+  const size_t na = (size_t)batch * M * K, nb = (size_t)batch * N * K, nc = (size_t)batch * M * N;
+  WL_CUDA(cudaMalloc((void**)&da, na * 2));
+  WL_CUDA(cudaMalloc((void**)&db, nb * 2));
+  WL_CUDA(cudaMalloc((void**)&dc, nc * 4));
+  WL_CUDA(cudaMemcpy(da, a_f16, na * 2, cudaMemcpyHostToDevice));
+  WL_CUDA(cudaMemcpy(db, b_f16, nb * 2, cudaMemcpyHostToDevice));
+  WL_CUDA(cudaMemset(dc, 0, nc * 4));
+  if (bias) {
+    WL_CUDA(cudaMalloc((void**)&dbias, (size_t)std::max(M, N) * 4));
+    WL_CUDA(cudaMemcpy(dbias, bias, (size_t)(transposed_store ? M : N) * 4, cudaMemcpyHostToDevice));
+  }
+  GemmEpilogue e;
+  e.out = dc; e.out_f32 = 1; e.gelu = gelu; e.bias = dbias;
+  if (transposed_store) { e.ldm = 1; e.ldn = M; e.bias_on_m = 1; }   // C^T stored: [N][M]
+  else { e.ldm = N; e.ldn = 1; }
+  e.ob1 = (long)M * N;
+  try {
+    GemmOperand A = opnd(da, M, K, K, batch, (long)M * K), Bo = opnd(db, N, K, K, batch, (long)N * K);
+    if (use_simt) gemm_tn_simt(c->st, A, Bo, M, N, K, e);
+    else gemm_tn(c->st, A, Bo, M, N, K, e);
+    WL_CUDA(cudaStreamSynchronize(c->st));
+    WL_CUDA(cudaMemcpy(cc, dc, nc * 4, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    cudaFree(da); cudaFree(db); cudaFree(dc); if (dbias) cudaFree(dbias);
+    throw;
+  }
+  cudaFree(da); cudaFree(db); cudaFree(dc); if (dbias) cudaFree(dbias);
+  API_END(c)
+}

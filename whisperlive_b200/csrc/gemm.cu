@@ -1,0 +1,383 @@
+// tcgen05 GEMM: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (single issuing thread) -> TMEM
+// accumulator -> tcgen05.ld epilogue (bias / GELU / residual / layout transforms fused).
+//
+// CTA = 256 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps4-7 epilogue
+// (thread i of the epilogue group owns accumulator row i = TMEM lane i).  Tile 128 x BN x 64.
+#include "gemm.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace wl {
+
+static std::atomic<long> g_gemm_launches{0};
+long gemm_launch_count() { return g_gemm_launches.load(); }
+
+struct GemmKParams {
+  int M, N, K;
+  int zn1;  // grid z = i1 + zn1 * i2
+  int a_batched, b_batched;
+  GemmEpilogue e;
+  int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 halves = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int cnt>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2) {
+  const GemmEpilogue& e = p.e;
+  if (m >= p.M) return;
+  if constexpr (cnt >= 8) if (e.mode == GEMM_HEADSPLIT) {
+    // m = (b, s), n = (h, dd); one thread writes cnt (<=32) consecutive dd of one head row
+    const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
+    const int h = n0 >> 6, dd = n0 & 63;
+    __half* dst = (__half*)e.out + (long)e.hs_slots[b] * e.hs_slot_stride + ((long)h * e.hs_S + s) * 64 + dd;
+#pragma unroll
+    for (int i = 0; i < cnt; i += 8) {
+      if (n0 + i >= p.N) break;
+      __align__(16) __half2 h2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = __uint_as_float(v[i + 2 * j]), c = __uint_as_float(v[i + 2 * j + 1]);
+        if (e.bias) {
+          a += e.bias[n0 + i + 2 * j];
+          c += e.bias[n0 + i + 2 * j + 1];
+        }
+        h2[j] = __floats2half2_rn(a, c);
+      }
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(h2);
+    }
+    return;
+  }
+  const long obase = (long)i1 * e.ob1 + (long)i2 * e.ob2 + m * e.ldm;
+  const long rbase = (long)i1 * e.rb1 + (long)i2 * e.rb2 + m * e.rldm;
+  const float bm = (e.bias && e.bias_on_m) ? e.bias[m] : 0.f;
+  if constexpr (cnt >= 8) if (p.vec_ok) {
+#pragma unroll
+    for (int i = 0; i < cnt; i += 8) {
+      const int n = n0 + i;
+      if (n >= p.N) break;
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[i + j]) + bm;
+      if (e.bias && !e.bias_on_m) {
+        const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+      if (e.gelu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+      }
+      if (e.resid) {
+        const float* r = e.resid + rbase + n;
+        const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+      }
+      if (e.out_f32) {
+        float* o = (float*)e.out + obase + n;
+        *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+        __align__(16) __half2 h2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        *reinterpret_cast<uint4*>((__half*)e.out + obase + n) = *reinterpret_cast<const uint4*>(h2);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < cnt; ++i) {
+    const int n = n0 + i;
+    if (n >= p.N) break;
+    float x = __uint_as_float(v[i]) + bm;
+    if (e.bias && !e.bias_on_m) x += e.bias[n];
+    if (e.gelu) x = gelu_erf(x);
+    if (e.resid) x += e.resid[rbase + (long)n * e.rldn];
+    const long o = obase + (long)n * e.ldn;
+    if (e.out_f32) ((float*)e.out)[o] = x;
+    else ((__half*)e.out)[o] = __float2half_rn(x);
+  }
+}
+
+template <int BN, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  uint8_t* sA = base;
+  uint8_t* sB = base + STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
+  const int i1 = z % p.zn1, i2 = z / p.zn1;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
+      const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, tile_m * BM, a1, a2);
+        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kb * BK, tile_n * BN, b1, b2);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 halves = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4) units
+          umma_f16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const long m = (long)tile_m * BM + q * 32 + lane_id();
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    if constexpr (BN >= 32) {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + c, v);
+        tmem_ld_wait();
+        epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2);
+      }
+    } else {
+      uint32_t v[16];
+      tmem_ld_32x16(lane_addr, v);
+      tmem_ld_wait();
+      epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_acc, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  });
+  WL_CHECK(fn != nullptr, WL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  long rows, k, ld, s1, s2;
+  int n1, n2, box_rows;
+  bool operator<(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) < 0; }
+};
+
+static const CUtensorMap& get_tmap(const GemmOperand& op, int box_rows) {
+  static std::map<TmapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = op.ptr; key.rows = op.rows; key.k = op.k; key.ld = op.ld; key.s1 = op.s1; key.s2 = op.s2;
+  key.n1 = op.n1; key.n2 = op.n2; key.box_rows = box_rows;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  WL_CHECK(((uintptr_t)op.ptr & 15) == 0, WL_ERR_ARG, "GEMM operand pointer must be 16-byte aligned");
+  WL_CHECK((op.ld * 2) % 16 == 0, WL_ERR_ARG, "GEMM operand row stride %ld elements is not a multiple of 16 bytes", op.ld);
+  const long s1 = op.n1 > 1 ? op.s1 : op.ld * op.rows, s2 = op.n2 > 1 ? op.s2 : s1 * op.n1;
+  WL_CHECK((s1 * 2) % 16 == 0 && (s2 * 2) % 16 == 0, WL_ERR_ARG, "GEMM operand batch strides must be multiples of 16 bytes");
+  cuuint64_t dims[4] = {(cuuint64_t)op.k, (cuuint64_t)op.rows, (cuuint64_t)op.n1, (cuuint64_t)op.n2};
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(s1 > 0 ? s1 : op.ld) * 2, (cuuint64_t)(s2 > 0 ? s2 : op.ld) * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op.ptr, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WL_CHECK(r == CUDA_SUCCESS, WL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%ld k=%ld ld=%ld n1=%d n2=%d", (int)r,
+           op.rows, op.k, op.ld, op.n1, op.n2);
+  if (cache.size() > 8192) cache.clear();
+  return cache.emplace(key, tm).first->second;
+}
+
+template <int BN, int STAGES, int MIN_CTAS>
+static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), Z);
+  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 256, smem, stream>>>(ta, tb, p);
+  WL_CUDA(cudaGetLastError());
+  g_gemm_launches++;
+}
+
+template <int BN, int STAGES, int MIN_CTAS>
+static void prime_cfg() {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+
+// opt-in shared memory sizes must be set outside stream capture: done once from wl_init
+void gemm_prime() {
+  prime_cfg<16, 8, 1>();
+  prime_cfg<32, 8, 1>();
+  prime_cfg<64, 4, 2>();
+  prime_cfg<128, 3, 2>();
+  prime_cfg<256, 4, 1>();
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static GemmKParams make_params(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& epi,
+                               int* Z) {
+  WL_CHECK(M > 0 && N > 0 && K > 0, WL_ERR_ARG, "gemm_tn: empty problem %dx%dx%d", M, N, K);
+  const int za = A.n1 * A.n2, zb = B.n1 * B.n2;
+  WL_CHECK(za == 1 || zb == 1 || (A.n1 == B.n1 && A.n2 == B.n2), WL_ERR_ARG, "gemm_tn: batch shapes differ");
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.a_batched = za > 1; p.b_batched = zb > 1;
+  p.zn1 = za > 1 ? A.n1 : B.n1;
+  *Z = za > zb ? za : zb;
+  p.e = epi;
+  p.vec_ok = 0;
+  if (epi.mode == GEMM_STORE && epi.ldn == 1) {
+    const int a = epi.out_f32 ? 4 : 8;  // elements per 16 bytes
+    bool ok = ((uintptr_t)epi.out & 15) == 0 && epi.ldm % 8 == 0 && epi.ob1 % 8 == 0 && epi.ob2 % 8 == 0 && N % 8 == 0;
+    (void)a;
+    if (epi.bias && !epi.bias_on_m) ok = ok && ((uintptr_t)epi.bias & 15) == 0;
+    if (epi.resid)
+      ok = ok && epi.rldn == 1 && ((uintptr_t)epi.resid & 15) == 0 && epi.rldm % 4 == 0 && epi.rb1 % 4 == 0 && epi.rb2 % 4 == 0;
+    p.vec_ok = ok ? 1 : 0;
+  }
+  if (epi.mode == GEMM_HEADSPLIT) {
+    WL_CHECK(!epi.out_f32 && !epi.gelu && !epi.resid && !epi.bias_on_m && N % 64 == 0 && epi.hs_slots, WL_ERR_ARG,
+             "gemm_tn: bad head-split epilogue");
+  }
+  return p;
+}
+
+void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& epi) {
+  static const int force_simt = env_int("WLB200_GEMM_SIMT", 0);
+  if (force_simt) return gemm_tn_simt(stream, A, B, M, N, K, epi);
+  int Z;
+  GemmKParams p = make_params(A, B, M, N, K, epi, &Z);
+  static const int force_bn = env_int("WLB200_BN", 0);
+  int bn;
+  if (force_bn) bn = force_bn;
+  else if (N <= 16) bn = 16;
+  else if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else bn = 128;
+  if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
+  const CUtensorMap& ta = get_tmap(A, BM);
+  const CUtensorMap& tb = get_tmap(B, bn);
+  switch (bn) {
+    case 16: launch_cfg<16, 8, 1>(stream, ta, tb, p, Z); break;
+    case 32: launch_cfg<32, 8, 1>(stream, ta, tb, p, Z); break;
+    case 64: launch_cfg<64, 4, 2>(stream, ta, tb, p, Z); break;
+    case 128: launch_cfg<128, 3, 2>(stream, ta, tb, p, Z); break;
+    case 256: launch_cfg<256, 4, 1>(stream, ta, tb, p, Z); break;
+    default: WL_CHECK(false, WL_ERR_ARG, "unsupported BN %d", bn);
+  }
+}
+
+// ------------------------------------------------------------------------------------ SIMT reference
+__global__ void gemm_tn_simt_kernel(GemmOperand A, GemmOperand B, GemmKParams p) {
+  const long n = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long m = blockIdx.y;
+  const int z = blockIdx.z;
+  if (n >= p.N) return;
+  const int i1 = z % p.zn1, i2 = z / p.zn1;
+  const __half* a = A.ptr + (p.a_batched ? (long)i1 * A.s1 + (long)i2 * A.s2 : 0) + m * A.ld;
+  const __half* b = B.ptr + (p.b_batched ? (long)i1 * B.s1 + (long)i2 * B.s2 : 0) + n * B.ld;
+  float acc = 0.f;
+  const int ka = (int)(A.k < p.K ? A.k : p.K), kb = (int)(B.k < p.K ? B.k : p.K);
+  const int kk = ka < kb ? ka : kb;
+  for (int k = 0; k < kk; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
+  uint32_t v[1] = {__float_as_uint(acc)};
+  GemmKParams q = p;
+  q.vec_ok = 0;
+  if (q.e.mode == GEMM_HEADSPLIT) {
+    const GemmEpilogue& e = q.e;
+    const int bb = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
+    float x = acc + (e.bias ? e.bias[n] : 0.f);
+    ((__half*)e.out)[(long)e.hs_slots[bb] * e.hs_slot_stride + ((long)(n >> 6) * e.hs_S + s) * 64 + (n & 63)] = __float2half_rn(x);
+    return;
+  }
+  epilogue_chunk<1>(q, m, (int)n, v, i1, i2);
+}
+
+void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& epi) {
+  int Z;
+  GemmKParams p = make_params(A, B, M, N, K, epi, &Z);
+  dim3 grid(cdiv(N, 128), M, Z);
+  gemm_tn_simt_kernel<<<grid, 128, 0, stream>>>(A, B, p);
+  WL_CUDA(cudaGetLastError());
+  g_gemm_launches++;
+}
+
+}  // namespace wl

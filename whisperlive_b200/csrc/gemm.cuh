@@ -1,0 +1,54 @@
+// tcgen05 / TMA / TMEM GEMM used by every dense contraction on the hot path (K2-K9, K12).
+//   C[z][m][n] = epilogue( sum_k A[z][m][k] * B[z][n][k] )      fp16 in, fp32 accumulate
+// Both operands are K-major ("TN"): activations [rows, K] and nn.Linear weights [out, K].
+#pragma once
+#include "common.cuh"
+
+namespace wl {
+
+// One operand as a strided 4-D view (k fastest): element (k, r, i1, i2) at ptr[k + r*ld + i1*s1 + i2*s2].
+struct GemmOperand {
+  const __half* ptr = nullptr;
+  long rows = 0;      // M (for A) or N (for B)
+  long k = 0;         // contraction length seen by TMA (reads beyond it are zero-filled)
+  long ld = 0;        // elements between consecutive rows (may be < k: overlapping rows, conv-as-GEMM)
+  int n1 = 1;         // batch dims; grid z = i1 + n1*i2
+  long s1 = 0;
+  int n2 = 1;
+  long s2 = 0;
+};
+
+enum GemmMode : int {
+  GEMM_STORE = 0,      // out[z][m*ldm + n*ldn]
+  GEMM_HEADSPLIT = 1,  // cross-KV cache layout: row m=(b,s), col n=(h,dd) -> out[slot[b]][h][s][dd]
+};
+
+struct GemmEpilogue {
+  void* out = nullptr;
+  int out_f32 = 0;           // 1: float output, 0: __half
+  long ldm = 0, ldn = 1;     // element strides of the output (ldm=1 -> transposed / swap-AB store)
+  long ob1 = 0, ob2 = 0;     // output batch strides
+  const float* bias = nullptr;
+  int bias_on_m = 0;         // bias indexed by m (swap-AB) instead of n
+  int gelu = 0;              // exact erf GELU after bias
+  const float* resid = nullptr;  // fp32 residual added last; same indexing scheme as out
+  long rldm = 0, rldn = 1, rb1 = 0, rb2 = 0;
+  int mode = GEMM_STORE;
+  // GEMM_HEADSPLIT parameters
+  int hs_S = 0, hs_H = 0;
+  long hs_slot_stride = 0;
+  const int* hs_slots = nullptr;  // device: slot index per stream b
+};
+
+// Launch on `stream`. M/N/K are the logical sizes per batch entry. Throws wl::Error.
+void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K,
+             const GemmEpilogue& epi);
+
+// Plain CUDA-core reference of the same contract (debug/bisect aid on the GPU box, WLB200_GEMM=simt;
+// also what the GEMM unit test compares against on-device).
+void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K,
+                  const GemmEpilogue& epi);
+
+long gemm_launch_count();
+
+}  // namespace wl

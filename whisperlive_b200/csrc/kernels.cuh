@@ -1,0 +1,114 @@
+// Launchers for the non-GEMM kernels of libwlb200 (K1, LN/softmax/prep, K10, K11, K12, K14).
+#pragma once
+#include "common.cuh"
+
+namespace wl {
+
+constexpr int T_MAX = 448;      // decoder positions
+constexpr int S_ENC = 1500;     // encoder positions
+constexpr int S_PAD = 1536;     // padded key dimension for materialised attention scores
+constexpr int MAX_ROWS_PER_STREAM = 8;
+constexpr int MAX_HYPS = 16;
+constexpr int MAX_CAND = 16;    // 2 * beam, beam <= 8
+
+// ---------------------------------------------------------------------------- K1 mel
+struct MelTables {
+  const float* window;      // [400]
+  const float* twiddle;     // [400][2]
+  const float* filt;        // [n_mels][201]
+  const int* filt_range;    // [n_mels][2]
+  int n_mels;
+};
+void mel_forward(cudaStream_t st, const float* pcm, const long* pcm_off, float* out, const long* out_off, unsigned* gmax,
+                 const MelTables& t, int B, int max_frames);
+
+// ---------------------------------------------------------------------------- elementwise / normalisation
+// features f32 [B][n_mels][3000] -> fp16 [B][3002][n_mels] (rows 0 and 3001 are zero: conv padding)
+void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int n_mels);
+// y = LayerNorm(x) * gamma + beta ; x f32 [rows][d] -> y fp16 [rows][d] (and optionally f32 copy)
+void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32,
+                    long rows, int d);
+// scores f32 [rows][ld_in] (first n valid) -> softmax(scale * s) as fp16 [rows][ld_out], columns >= n zeroed
+void softmax_rows(cudaStream_t st, const float* s, __half* p, long rows, int n, int ld_in, int ld_out, float scale);
+
+// ---------------------------------------------------------------------------- decoder state (device resident)
+struct DecodeState {
+  // per row
+  int* tok_in;       // [R]
+  int* pos;          // [R] position of tok_in == tokens already cached for the row
+  int* active;       // [R]
+  float* cum;        // [R]
+  int* gen_len;      // [R]
+  int* last_ts;      // [R] last generated timestamp token or -1
+  int* row_done;     // [R]
+  int* hist;         // [R][T_MAX] generated tokens
+  short* src;        // [R][T_MAX] physical cache row holding position p of this row's sequence
+  // per-row candidates produced by search_rows
+  float* cand_val;   // [R][MAX_CAND]
+  int* cand_tok;     // [R][MAX_CAND]
+  float* nospeech_row;  // [R] softmax(raw logits)[no_speech] of the row (valid when computed)
+  // per stream
+  int* slot;         // [B]
+  int* prompt;       // [B][T_MAX]
+  int* prompt_len;   // [B]
+  int* fed;          // [B] index of the prompt token fed at the current step
+  int* sot_index;    // [B] or -1
+  int* use_ts;       // [B]
+  int* n_new;        // [B] max new tokens
+  int* step;         // [B] generation steps done
+  int* done;         // [B]
+  int* n_alive;      // [B]
+  float* no_speech;  // [B]
+  int* hyp_count;    // [B]
+  float* hyp_cum;    // [B][MAX_HYPS]
+  int* hyp_len;      // [B][MAX_HYPS]
+  int* hyp_tok;      // [B][MAX_HYPS][T_MAX]
+  int* steps_run;    // [B] decoder steps executed for the stream (diagnostics)
+  int* n_done;       // [1] number of finished streams
+  // teacher-forced mode (detect_language / align / logits test hook)
+  int* force_len;    // [B] 0 = normal search; >0 = feed prompt only, then stop
+  float* force_prob; // [B][T_MAX] P(prompt[i+1] | prompt[..i]) in teacher-forced mode
+};
+
+struct SearchOpts {
+  int beam;            // K (1 = greedy / sampling)
+  int rows_per_stream; // Kr
+  int max_cand;        // round(K * patience)
+  int suppress_blank;
+  int max_initial_ts;
+  int sampling;        // 1: Gumbel-max sampling over the full distribution
+  float temperature;
+  unsigned seed;
+  const unsigned* suppress_mask;  // device bitmask over the vocabulary
+};
+
+struct VocabIds {
+  int vocab, vocab_ld, eot, sot, no_speech, no_timestamps, ts_begin, blank;
+};
+
+// x[r] = E[tok_in[r]] + P[pos[r]]  (f32) for active rows; also src[r][pos[r]] = r
+void decoder_embed(cudaStream_t st, const DecodeState& s, const __half* emb, const __half* pos_emb, float* x, int R, int d);
+
+// K10: self attention over the KV cache with beam indirection. qkv f32 [R][3d]; out fp16 [R][d].
+void decoder_self_attn(cudaStream_t st, const DecodeState& s, const float* qkv, __half* kcache, __half* vcache,
+                       long cache_row_stride, __half* out, int R, int H, int d);
+
+// K11: cross attention of the rows of each stream over its persistent encoder K/V.
+//   q f32 [R][d]; K/V caches [slot][H][1500][64] fp16 (layer base pointers); out fp16 [R][d]
+struct CrossAttnWorkspace {
+  float* part;     // [B][H][nsplit][MAX_ROWS_PER_STREAM][66]  (m, l, o[64])
+  float* probs;    // optional [R][H][1500] f32 attention probabilities (align mode) or nullptr
+};
+void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
+                        long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
+                        int d, int nsplit);
+int cross_attn_pick_nsplit(int B, int H, int num_sms);
+
+// K12: per-row masked log-softmax + top candidates, then per-stream beam / greedy update.
+void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, const SearchOpts& o, const VocabIds& v, int R);
+void search_streams(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B);
+
+// initialise the state for a generate call (prompts already uploaded)
+void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R);
+
+}  // namespace wl

@@ -1,0 +1,31 @@
+// Launch accounting, kernel attribute priming and the K14 attention-probability gather.
+#include <atomic>
+
+#include "kernels.cuh"
+
+namespace wl {
+
+static std::atomic<long> g_other_launches{0};
+long other_launch_count() { return g_other_launches.load(); }
+void note_launch(int n) { g_other_launches += n; }
+
+// copy the cross-attention probabilities of the alignment heads that live in `layer`
+__global__ void gather_align_kernel(DecodeState s, const float* __restrict__ probs, float* __restrict__ buf,
+                                    const int* __restrict__ heads, int n_heads, int layer, int rows_per_stream, int H) {
+  const int b = blockIdx.y, i = blockIdx.x;
+  if (s.done[b] || heads[2 * i] != layer) return;
+  const int h = heads[2 * i + 1], r = b * rows_per_stream, pos = s.pos[r];
+  const float* src = probs + ((long)r * H + h) * S_ENC;
+  float* dst = buf + (((long)b * n_heads + i) * T_MAX + pos) * S_ENC;
+  for (int k = threadIdx.x; k < S_ENC; k += blockDim.x) dst[k] = src[k];
+}
+
+void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* probs, float* buf, const int* heads, int n_heads,
+                        int layer, int B, int rows_per_stream, int H) {
+  dim3 grid(n_heads, B);
+  gather_align_kernel<<<grid, 256, 0, st>>>(s, probs, buf, heads, n_heads, layer, rows_per_stream, H);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
+}  // namespace wl
