@@ -63,6 +63,7 @@ typedef struct wl_gen_opts {
   const int32_t* suppress_tokens;
   int32_t n_suppress;
   int32_t use_cuda_graph;            /* 1: capture the decoder step once per call shape */
+  const int32_t* max_length_per_stream; /* optional [B]: overrides max_length per stream (ragged max_new_tokens) */
 } wl_gen_opts;
 
 int wl_init(const wl_config* cfg, wl_ctx** out);

@@ -1,0 +1,189 @@
+"""CPU tests of the drop-in boundary: C-ABI export list, plugin surface (ServeClientB200 on the
+reference's own ServeClientBase), scheduler batching, and the multi-rank stream sharding (gloo)."""
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF = "/root/reference"
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The library loads without a GPU and exports exactly what include/wlb200.h declares."""
+    from whisperlive_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "wlb200.h")).read()
+    declared = set(re.findall(r"\b(wl_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (wl_[a-z_]+)", out))
+    assert declared <= exported
+
+
+def test_wl_init_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from whisperlive_b200.config import dims_for
+    from whisperlive_b200.engine import B200Whisper
+    from whisperlive_b200 import _lib
+    with pytest.raises(_lib.WlError, match="no CUDA device|no CPU fallback"):
+        B200Whisper(dims_for("micro.en"), {}, max_streams=1, max_beam=1)
+
+
+def test_product_never_imports_oracle():
+    """No module under whisperlive_b200/ may import the oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "whisperlive_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def _oracle_model(name="micro.en", seed=0):
+    from oracle.engine import OracleWhisper
+    from oracle.mel import OracleFeatureExtractor
+    from whisperlive_b200.config import dims_for
+    from whisperlive_b200.tokenizer import build_synthetic_tokenizer
+    from whisperlive_b200.transcriber import B200WhisperModel
+    from whisperlive_b200.weights import random_init
+    dims = dims_for(name)
+    return B200WhisperModel(name, engine=OracleWhisper(random_init(dims, seed=seed), dims),
+                            hf_tokenizer=build_synthetic_tokenizer(dims.vocab),
+                            feature_extractor=OracleFeatureExtractor(dims.n_mels))
+
+
+def test_scheduler_batches_and_survives_errors():
+    from whisperlive_b200.scheduler import BatchRequest, StreamScheduler
+
+    class Fake:
+        def __init__(self):
+            self.calls = []
+
+        def transcribe_batch(self, audios, kws):
+            self.calls.append(len(audios))
+            if any(len(a) == 13 for a in audios):
+                raise RuntimeError("boom")
+            return [([f"seg{len(a)}"], "info") for a in audios]
+    fake = Fake()
+    sch = StreamScheduler(fake, max_batch_size=4, batch_window_ms=200)
+    sch.start()
+    reqs = [BatchRequest(audio=np.zeros(n, np.float32), use_vad=False) for n in (5, 6, 7)]
+    for r in reqs:
+        sch.submit(r)
+    assert all(r.future.wait(5) for r in reqs)
+    assert [r.result for r in reqs] == [["seg5"], ["seg6"], ["seg7"]] and fake.calls == [3]
+    bad = BatchRequest(audio=np.zeros(13, np.float32))
+    sch.submit(bad)
+    assert bad.future.wait(5) and isinstance(bad.error, RuntimeError)
+    ok = BatchRequest(audio=np.zeros(2, np.float32))
+    sch.submit(ok)
+    assert ok.future.wait(5) and ok.result == ["seg2"]   # worker is still alive
+    sch.stop()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_backend_plugin_streams_segments_through_reference_base():
+    """ServeClientB200 subclasses the reference's ServeClientBase; frames go in through add_frames and
+    segment JSON comes out of the reference's own send path."""
+    sys.path.insert(0, REF)
+    try:
+        from whisperlive_b200 import synth
+        from whisperlive_b200.backend import ServeClientB200
+        from whisper_live.backend.base import ServeClientBase
+    finally:
+        sys.path.remove(REF)
+    assert issubclass(ServeClientB200, ServeClientBase)
+    torch.set_num_threads(8)
+
+    class WS:
+        def __init__(self):
+            self.sent, self.closed = [], False
+
+        def send(self, msg):
+            self.sent.append(json.loads(msg))
+
+        def close(self):
+            self.closed = True
+    model = _oracle_model()
+    orig = model.transcribe_batch
+    model.transcribe_batch = lambda audios, kws: orig(audios, [dict(k, temperature=[0.0], beam_size=2, log_prob_threshold=None,
+                                                                         max_new_tokens=24) for k in kws])
+    ServeClientB200.MODEL_FACTORY = lambda name: model
+    ws = WS()
+    try:
+        client = ServeClientB200(ws, client_uid="u1", model="micro.en", use_vad=False, no_speech_thresh=1.1)
+        assert ws.sent[0] == {"uid": "u1", "message": "SERVER_READY", "backend": "faster_whisper"}
+        assert client.language == "en"
+        client.add_frames(synth.speech_like(3.0, seed=1))
+        deadline = time.time() + 60
+        while time.time() < deadline and not any("segments" in m for m in ws.sent):
+            time.sleep(0.1)
+        client.exit = True
+        client.trans_thread.join(timeout=30)
+        segs = [m for m in ws.sent if "segments" in m]
+        assert segs, ws.sent
+        s0 = segs[0]["segments"][0]
+        assert set(s0) >= {"start", "end", "text", "completed"} and segs[0]["uid"] == "u1"
+    finally:
+        ServeClientB200.shutdown()
+        ServeClientB200.MODEL_FACTORY = None
+
+
+GLOO_WORKER = r"""
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from tests.test_boundary_cpu import _oracle_model
+from whisperlive_b200 import synth
+torch.set_num_threads(2)
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+n_streams = 3
+waves = [synth.speech_like(2.0 + i, seed=40 + i) for i in range(n_streams)]
+mine = [i for i in range(n_streams) if i % world == rank]
+model = _oracle_model()
+kw = dict(temperature=[0.0], beam_size=2, log_prob_threshold=None, max_new_tokens=16)
+out = model.transcribe_batch([waves[i] for i in mine], [kw] * len(mine))
+ids = [[t for s in segs for t in s.tokens] for segs, _ in out]
+flat = torch.full((n_streams, 64), -1, dtype=torch.int32)
+for i, seq in zip(mine, ids):
+    flat[i, :len(seq)] = torch.tensor(seq, dtype=torch.int32)
+gathered = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat)            # one collective per batch: emitted token ids
+merged = torch.stack(gathered).max(0).values
+if rank == 0:
+    print("RESULT " + json.dumps(merged.tolist()))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_stream_sharding_matches_single_process(tmp_path):
+    """world_size=2 (gloo): streams sharded round-robin, token ids all-gathered; equals 1-process output."""
+    from whisperlive_b200 import synth
+    torch.set_num_threads(4)
+    model = _oracle_model()
+    kw = dict(temperature=[0.0], beam_size=2, log_prob_threshold=None, max_new_tokens=16)
+    waves = [synth.speech_like(2.0 + i, seed=40 + i) for i in range(3)]
+    single = [[t for s in segs for t in s.tokens] for segs, _ in model.transcribe_batch(waves, [kw] * 3)]
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = next(l for l in outs[0][0].splitlines() if l.startswith("RESULT "))
+    merged = json.loads(line[len("RESULT "):])
+    for i, seq in enumerate(single):
+        assert [t for t in merged[i] if t >= 0] == seq

@@ -36,6 +36,7 @@ class WlGenOpts(C.Structure):
         ("max_length", C.c_int32), ("suppress_blank", C.c_int32), ("max_initial_timestamp_index", C.c_int32),
         ("sampling_topk", C.c_int32), ("sampling_temperature", C.c_float), ("seed", C.c_uint32),
         ("suppress_tokens", c_i32p), ("n_suppress", C.c_int32), ("use_cuda_graph", C.c_int32),
+        ("max_length_per_stream", c_i32p),
     ]
 
 

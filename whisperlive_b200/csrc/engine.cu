@@ -366,7 +366,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->EB = std::min(c->Bm, 8);
   c->AB = std::min(c->EB, d >= 1024 ? 2 : 4);
   const size_t M = (size_t)c->EB * S_ENC;
-  c->feat32 = dalloc<float>(c, (size_t)c->EB * nm * 3000);
+  c->feat32 = dalloc<float>(c, (size_t)c->Bm * nm * 3000);  // all streams of a call stay resident (wl_encode_resident)
   c->feat16 = dalloc<__half>(c, (size_t)c->EB * 3002 * nm + 4096);
   c->conv1o = dalloc<__half>(c, (size_t)c->EB * 3002 * d + 4096);
   c->x = dalloc<float>(c, M * d);
@@ -479,11 +479,11 @@ static GemmOperand opnd(const __half* p, long rows, long k, long ld, int n1 = 1,
   return o;
 }
 
-static void encoder_pass(wl_ctx* c, int nb, const int* slots_host) {
+static void encoder_pass(wl_ctx* c, int nb, const int* slots_host, const float* feat_dev) {
   const int d = c->d, H = c->H, nm = c->n_mels, ff = 4 * c->d;
   const long M = (long)nb * S_ENC;
   cudaStream_t st = c->st;
-  prep_features(st, c->feat32, c->feat16, nb, nm);
+  prep_features(st, feat_dev, c->feat16, nb, nm);
   {  // conv1 + GELU -> conv1o rows 1..3000 (rows 0 / 3001 stay zero)
     GemmEpilogue e;
     e.out = c->conv1o + d; e.out_f32 = 0; e.ldm = d; e.ldn = 1; e.ob1 = 3002L * d; e.bias = c->b_conv1; e.gelu = 1;
@@ -566,10 +566,10 @@ static void encode_impl(wl_ctx* c, const float* features_host, int B, const int*
   for (int b0 = 0; b0 < B; b0 += c->EB) {
     const int nb = std::min(c->EB, B - b0);
     if (!resident)
-      WL_CUDA(cudaMemcpyAsync(c->feat32, features_host + b0 * per, nb * per * sizeof(float), cudaMemcpyHostToDevice, c->st));
+      WL_CUDA(cudaMemcpyAsync(c->feat32 + b0 * per, features_host + b0 * per, nb * per * sizeof(float), cudaMemcpyHostToDevice, c->st));
     WL_CUDA(cudaMemcpyAsync(c->enc_slots_dev, slots + b0, nb * sizeof(int), cudaMemcpyHostToDevice, c->st));
     WL_CUDA(cudaEventRecord(c->ev0, c->st));
-    encoder_pass(c, nb, slots + b0);
+    encoder_pass(c, nb, slots + b0, c->feat32 + b0 * per);
     WL_CUDA(cudaEventRecord(c->ev1, c->st));
     WL_CUDA(cudaStreamSynchronize(c->st));
     float ms;
@@ -600,7 +600,7 @@ extern "C" int wl_encode(wl_ctx* c, const float* features, int32_t B, int32_t* s
 
 extern "C" int wl_encode_resident(wl_ctx* c, int32_t B, const int32_t* slots) {
   API_BEGIN(c)
-  WL_CHECK(B >= 1 && B <= c->EB, WL_ERR_ARG, "wl_encode_resident: B must be <= %d", c->EB);
+  WL_CHECK(B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_encode_resident: B must be <= %d", c->Bm);
   for (int b = 0; b < B; ++b) WL_CHECK(slots[b] >= 0 && slots[b] < c->NS && c->slot_used[slots[b]], WL_ERR_ARG, "bad slot");
   encode_impl(c, nullptr, B, slots, true);
   API_END(c)
@@ -708,7 +708,7 @@ static VocabIds vocab_ids(wl_ctx* c) {
 
 // upload prompts & per-stream metadata; returns max steps
 static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t* prompts, const int32_t* off, int max_length,
-                          bool forced) {
+                          bool forced, const int32_t* max_len_ps = nullptr) {
   ensure_host(c, (size_t)B * (T_MAX + 8), 16);
   int* hp = c->h_int;                      // [B][T_MAX]
   int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len  (6 x B)
@@ -726,8 +726,10 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
     }
     int n_new = 0;
     if (!forced) {
-      n_new = std::min(max_length / 2, max_length - P);
-      WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, max_length);
+      const int ml = max_len_ps ? max_len_ps[b] : max_length;
+      WL_CHECK(ml >= 2 && ml <= T_MAX, WL_ERR_ARG, "stream %d: max_length %d out of range", b, ml);
+      n_new = std::min(ml / 2, ml - P);
+      WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, ml);
       max_steps = std::max(max_steps, P - 1 + n_new);
     } else {
       max_steps = std::max(max_steps, P);
@@ -781,7 +783,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     const int t = o->suppress_tokens[i];
     if (t >= 0 && t < c->V) mask[t >> 5] |= 1u << (t & 31);
   }
-  const int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false);
+  const int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false, o->max_length_per_stream);
   WL_CUDA(cudaMemcpyAsync(c->suppress_mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaEventRecord(c->ev0, st));
   decode_init(st, c->ds, so, vi, B, R);

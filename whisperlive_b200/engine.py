@@ -238,7 +238,7 @@ class B200Whisper:
                  no_repeat_ngram_size: int = 0, max_length: int = 448, return_scores: bool = False,
                  return_no_speech_prob: bool = False, max_initial_timestamp_index: int = 50, suppress_blank: bool = True,
                  suppress_tokens: Optional[Sequence[int]] = (-1,), sampling_topk: int = 1, sampling_temperature: float = 1,
-                 seed: int = 0) -> List[WhisperGenerationResult]:
+                 seed: int = 0, max_length_per_stream: Optional[Sequence[int]] = None) -> List[WhisperGenerationResult]:
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size other than the reference's 1 / 0")
         enc = self._as_encoded(features)
@@ -260,7 +260,11 @@ class B200Whisper:
                 max_initial_timestamp_index=int(max_initial_timestamp_index), sampling_topk=int(sampling_topk),
                 sampling_temperature=float(sampling_temperature), seed=int(seed) & 0xFFFFFFFF,
                 suppress_tokens=_lib.ptr(sup, C.c_int32) if len(sup) else None, n_suppress=len(sup),
-                use_cuda_graph=int(self.use_cuda_graph))
+                use_cuda_graph=int(self.use_cuda_graph), max_length_per_stream=None)
+            mlps = None
+            if max_length_per_stream is not None:
+                mlps = np.asarray(list(max_length_per_stream)[b0:b0 + B], dtype=np.int32)
+                opts.max_length_per_stream = _lib.ptr(mlps, C.c_int32)
             ids = np.zeros((B, NH, T_MAX), dtype=np.int32)
             lens = np.zeros((B, NH), dtype=np.int32)
             score = np.zeros((B, NH), dtype=np.float32)
@@ -279,6 +283,7 @@ class B200Whisper:
                         seqs.append(ids[b, h, :lens[b, h]].tolist())
                         scs.append(float(score[b, h]))
                 results.append(WhisperGenerationResult(seqs, scs, float(nsp[b]), int(steps[b])))
+        self.last_steps = max((r.steps for r in results), default=0)
         return results
 
     # ------------------------------------------------------------------ ctranslate2.models.Whisper.detect_language

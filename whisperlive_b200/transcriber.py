@@ -660,13 +660,19 @@ class B200WhisperModel:
             pending = list(range(len(live)))
             while pending:
                 # group streams whose generate() arguments are identical (temperature rung, beam, ...)
+                # (max_length may differ per stream -- ragged max_new_tokens -- and is passed per stream)
                 groups: Dict[str, List[int]] = {}
+                kwargs = {k: live[k][0].generate_kwargs() for k in pending}
                 for k in pending:
-                    kw = live[k][0].generate_kwargs()
-                    groups.setdefault(json.dumps(kw, sort_keys=True, default=list), []).append(k)
+                    key = {a: v for a, v in kwargs[k].items() if a != "max_length"}
+                    groups.setdefault(json.dumps(key, sort_keys=True, default=list), []).append(k)
                 nxt = []
                 for _key, ks in groups.items():
-                    kw = live[ks[0]][0].generate_kwargs()
+                    kw = dict(kwargs[ks[0]])
+                    lengths = [kwargs[k]["max_length"] for k in ks]
+                    if len(set(lengths)) > 1:
+                        kw["max_length_per_stream"] = lengths
+                        kw["max_length"] = max(lengths)
                     sub = enc.select(ks) if hasattr(enc, "select") else _EncoderSlice(enc, ks)
                     outs = self.model.generate(sub, [live[k][0].prompt for k in ks], **kw)
                     for k, r in zip(ks, outs):
