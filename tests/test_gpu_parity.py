@@ -24,7 +24,7 @@ from whisperlive_b200.weights import random_init
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 0.12       # fp16 logit tolerance (logit std is ~3)
-MARGIN_TOL = 0.12      # a token/beam decision closer than this may legitimately flip
+MARGIN_TOL = 0.20      # a token/beam decision closer than this may legitimately flip (two rows' logit errors add)
 
 _ENGINES = {}
 
@@ -233,7 +233,7 @@ def test_generate_options_and_errors():
     _compare_generation(got, ref, "options")
     assert all(len(s) <= 20 for s in got[0].sequences_ids)
     with pytest.raises(RuntimeError):
-        eng.generate(enc, [[sp.sot] * 447], beam_size=1)            # no room under max_length
+        eng.generate(enc, [[sp.sot] * 448], beam_size=1)            # no room under max_length
     with pytest.raises(RuntimeError):
         eng.generate(enc, [[dims.vocab + 5]], beam_size=1)          # token out of range
     with pytest.raises(ValueError):
@@ -243,7 +243,9 @@ def test_generate_options_and_errors():
 
 
 def test_slot_pool_accounting():
+    import gc
     eng, _ = engine("micro.en", seed=0)
+    gc.collect()
     free0 = eng.free_slots()
     enc = eng.encode(feats_for(eng.dims, 2.0, 1)[None])
     assert eng.free_slots() == free0 - 1

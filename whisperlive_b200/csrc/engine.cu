@@ -1096,3 +1096,36 @@ extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_
   cudaFree(da); cudaFree(db); cudaFree(dc); if (dbias) cudaFree(dbias);
   API_END(c)
 }
+
+extern "C" int wl_bench_gemm(wl_ctx* c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t transposed_store,
+                             float* ms_out) {
+  API_BEGIN(c)
+  WL_CHECK(ms_out && M > 0 && N > 0 && K > 0 && batch > 0 && iters > 0, WL_ERR_ARG, "wl_bench_gemm: bad arguments");
+  __half *da = nullptr, *db = nullptr, *dc = nullptr;
+  const size_t na = (size_t)batch * M * K, nb = (size_t)batch * N * K, nc = (size_t)batch * M * N;
+  WL_CUDA(cudaMalloc((void**)&da, na * 2));
+  WL_CUDA(cudaMalloc((void**)&db, nb * 2));
+  WL_CUDA(cudaMalloc((void**)&dc, nc * 2));
+  WL_CUDA(cudaMemset(da, 0x11, na * 2));
+  WL_CUDA(cudaMemset(db, 0x11, nb * 2));
+  GemmEpilogue e;
+  e.out = dc; e.out_f32 = 0;
+  if (transposed_store) { e.ldm = 1; e.ldn = M; } else { e.ldm = N; e.ldn = 1; }
+  e.ob1 = (long)M * N;
+  try {
+    GemmOperand A = opnd(da, M, K, K, batch, (long)M * K), Bo = opnd(db, N, K, K, batch, (long)N * K);
+    for (int i = 0; i < 3; ++i) gemm_tn(c->st, A, Bo, M, N, K, e);
+    WL_CUDA(cudaEventRecord(c->ev0, c->st));
+    for (int i = 0; i < iters; ++i) gemm_tn(c->st, A, Bo, M, N, K, e);
+    WL_CUDA(cudaEventRecord(c->ev1, c->st));
+    WL_CUDA(cudaStreamSynchronize(c->st));
+    float ms;
+    WL_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_out = ms / iters;
+  } catch (...) {
+    cudaFree(da); cudaFree(db); cudaFree(dc);
+    throw;
+  }
+  cudaFree(da); cudaFree(db); cudaFree(dc);
+  API_END(c)
+}

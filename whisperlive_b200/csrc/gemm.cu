@@ -5,6 +5,7 @@
 // (thread i of the epilogue group owns accumulator row i = TMEM lane i).  Tile 128 x BN x 64.
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,7 @@ struct GemmKParams {
   int M, N, K;
   int zn1;  // grid z = i1 + zn1 * i2
   int a_batched, b_batched;
+  int a_pos[3], b_pos[3];  // tensor-map coordinate slots (1..3) of (row, i1, i2)
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
 };
@@ -155,11 +157,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
       const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
+      int ca[4] = {0, 0, 0, 0}, cb[4] = {0, 0, 0, 0};
+      ca[p.a_pos[0]] = tile_m * BM; ca[p.a_pos[1]] = a1; ca[p.a_pos[2]] = a2;
+      cb[p.b_pos[0]] = tile_n * BN; cb[p.b_pos[1]] = b1; cb[p.b_pos[2]] = b2;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, tile_m * BM, a1, a2);
-        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kb * BK, tile_n * BN, b1, b2);
+        ca[0] = cb[0] = kb * BK;
+        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], ca[0], ca[1], ca[2], ca[3]);
+        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], cb[0], cb[1], cb[2], cb[3]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -234,8 +240,16 @@ struct TmapKey {
   bool operator<(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) < 0; }
 };
 
-static const CUtensorMap& get_tmap(const GemmOperand& op, int box_rows) {
-  static std::map<TmapKey, CUtensorMap> cache;
+// Tensor map + where the (row, i1, i2) coordinates sit among its dims 1..3.  TMA wants strides in
+// ascending order (each a multiple of the previous), so the view's dims are sorted by stride: e.g. the
+// per-head Q/K operand of attention is {k, head (128 B), row (2*ld B), batch}.
+struct TmapInfo {
+  CUtensorMap tm;
+  int pos[3];
+};
+
+static TmapInfo get_tmap(const GemmOperand& op, int box_rows) {
+  static std::map<TmapKey, TmapInfo> cache;
   static std::mutex mu;
   TmapKey key;
   memset(&key, 0, sizeof(key));
@@ -245,21 +259,39 @@ static const CUtensorMap& get_tmap(const GemmOperand& op, int box_rows) {
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   WL_CHECK(((uintptr_t)op.ptr & 15) == 0, WL_ERR_ARG, "GEMM operand pointer must be 16-byte aligned");
-  WL_CHECK((op.ld * 2) % 16 == 0, WL_ERR_ARG, "GEMM operand row stride %ld elements is not a multiple of 16 bytes", op.ld);
-  const long s1 = op.n1 > 1 ? op.s1 : op.ld * op.rows, s2 = op.n2 > 1 ? op.s2 : s1 * op.n1;
-  WL_CHECK((s1 * 2) % 16 == 0 && (s2 * 2) % 16 == 0, WL_ERR_ARG, "GEMM operand batch strides must be multiples of 16 bytes");
-  cuuint64_t dims[4] = {(cuuint64_t)op.k, (cuuint64_t)op.rows, (cuuint64_t)op.n1, (cuuint64_t)op.n2};
-  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, (cuuint64_t)(s1 > 0 ? s1 : op.ld) * 2, (cuuint64_t)(s2 > 0 ? s2 : op.ld) * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  struct D { long size, stride; int role; };
+  std::vector<D> real, single;
+  const D all[3] = {{op.rows, op.ld, 0}, {op.n1, op.s1, 1}, {op.n2, op.s2, 2}};
+  for (const D& d : all) ((d.role == 0 || d.size > 1) ? real : single).push_back(d);
+  std::stable_sort(real.begin(), real.end(), [](const D& x, const D& y) { return x.stride < y.stride; });
+  std::vector<D> order = real;
+  for (D d : single) {
+    d.stride = order.back().stride * order.back().size;
+    order.push_back(d);
+  }
+  TmapInfo info;
+  cuuint64_t dims[4] = {(cuuint64_t)op.k, 1, 1, 1};
+  cuuint64_t strides[3];
+  cuuint32_t box[4] = {(cuuint32_t)BK, 1, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMap tm;
-  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op.ptr, dims, strides, box, estr,
+  for (int i = 0; i < 3; ++i) {
+    WL_CHECK(order[i].stride > 0 && (order[i].stride * 2) % 16 == 0, WL_ERR_ARG,
+             "GEMM operand stride %ld elements (dim role %d) is not a positive multiple of 16 bytes", order[i].stride, order[i].role);
+    dims[1 + i] = (cuuint64_t)order[i].size;
+    strides[i] = (cuuint64_t)order[i].stride * 2;
+    if (order[i].role == 0) box[1 + i] = (cuuint32_t)box_rows;
+    info.pos[order[i].role] = 1 + i;
+  }
+  CUresult r = encode_fn()(&info.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op.ptr, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  WL_CHECK(r == CUDA_SUCCESS, WL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%ld k=%ld ld=%ld n1=%d n2=%d", (int)r,
-           op.rows, op.k, op.ld, op.n1, op.n2);
+  WL_CHECK(r == CUDA_SUCCESS, WL_ERR_CUDA,
+           "cuTensorMapEncodeTiled failed (%d) dims={%llu,%llu,%llu,%llu} strides={%llu,%llu,%llu} box_rows=%d", (int)r,
+           (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+           (unsigned long long)strides[0], (unsigned long long)strides[1], (unsigned long long)strides[2], box_rows);
   if (cache.size() > 8192) cache.clear();
-  return cache.emplace(key, tm).first->second;
+  cache.emplace(key, info);
+  return info;
 }
 
 template <int BN, int STAGES, int MIN_CTAS>
@@ -333,8 +365,10 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   else if (N <= 64) bn = 64;
   else bn = 128;
   if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
-  const CUtensorMap& ta = get_tmap(A, BM);
-  const CUtensorMap& tb = get_tmap(B, bn);
+  const TmapInfo ia = get_tmap(A, BM), ib = get_tmap(B, bn);
+  const CUtensorMap& ta = ia.tm;
+  const CUtensorMap& tb = ib.tm;
+  for (int i = 0; i < 3; ++i) { p.a_pos[i] = ia.pos[i]; p.b_pos[i] = ib.pos[i]; }
   switch (bn) {
     case 16: launch_cfg<16, 8, 1>(stream, ta, tb, p, Z); break;
     case 32: launch_cfg<32, 8, 1>(stream, ta, tb, p, Z); break;
