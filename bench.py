@@ -192,7 +192,7 @@ def main():
     n_local = len(mine)
     heads = [(dims.dec_layers - 1 - (i // 4), (3 * i) % dims.n_heads) for i in range(10)]
     eng = B200Whisper(dims, random_init(dims, seed=0), device_index=local, max_streams=max(1, n_local), max_beam=max(args.beam, 1),
-                      enc_slots=max(1, n_local) + 2, alignment_heads=heads)
+                      enc_slots=2 * max(1, n_local) + 2, alignment_heads=heads)
     model = B200WhisperModel(args.model, engine=eng, hf_tokenizer=build_synthetic_tokenizer(dims.vocab),
                              feature_extractor=FeatureExtractor(eng, dims.n_mels))
     tok_eot = eng.eot

@@ -1,4 +1,6 @@
 // Row-wise helper kernels: feature layout prep, LayerNorm, softmax, decoder token embedding.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace wl {
@@ -42,7 +44,10 @@ void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int 
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ be, __half* __restrict__ y,
-                                                        float* __restrict__ y32, long rows, int d) {
+                                                        float* __restrict__ y32, long rows, int d, float* __restrict__ zero_buf,
+                                                        long zero_n) {
+  // optional side job: clear the fp32 buffer the next split-K GEMM accumulates into
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < zero_n; i += (long)gridDim.x * 256) zero_buf[i] = 0.f;
   const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -76,12 +81,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32, long rows,
-                    int d) {
+                    int d, float* zero_buf, long zero_n) {
   WL_CHECK(d <= 1280 && d % 32 == 0, WL_ERR_ARG, "layernorm: unsupported width %d", d);
-  const int grid = cdiv(rows, 8);
-  if (d <= 512) layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d);
-  else if (d <= 1024) layernorm_kernel<32><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d);
-  else layernorm_kernel<40><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d);
+  int grid = cdiv(rows, 8);
+  if (zero_buf && zero_n > 0) grid = std::max(grid, std::min(148, cdiv(zero_n, 256 * 16)));
+  if (d <= 512) layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
+  else if (d <= 1024) layernorm_kernel<32><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
+  else layernorm_kernel<40><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
+// ---------------------------------------------------------------------------- gelu_cast
+__global__ void gelu_cast_kernel(const float* __restrict__ in, __half* __restrict__ out, long n) {
+  const long i = (blockIdx.x * 256L + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(in + i);
+  __align__(8) __half2 h[2] = {__floats2half2_rn(gelu_erf(v.x), gelu_erf(v.y)), __floats2half2_rn(gelu_erf(v.z), gelu_erf(v.w))};
+  *reinterpret_cast<uint2*>(out + i) = *reinterpret_cast<const uint2*>(h);
+}
+
+void gelu_cast(cudaStream_t st, const float* in, __half* out, long n) {
+  WL_CHECK(n % 4 == 0, WL_ERR_ARG, "gelu_cast: n must be a multiple of 4");
+  gelu_cast_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(in, out, n);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

@@ -2,6 +2,7 @@
 // the C ABI declared in include/wlb200.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -16,6 +17,8 @@ using namespace wl;
 namespace wl {
 void gemm_prime();
 void attention_prime();
+void flash_attn_prime();
+void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt, __half* out, int nb, int H, int d);
 long other_launch_count();
 }  // namespace wl
 
@@ -76,7 +79,7 @@ struct wl_ctx {
   std::vector<int> slot_free;
   std::vector<char> slot_used;
   // decoder workspaces
-  float *dx, *dqkv, *dqc, *logits;
+  float *dx, *dqkv, *dqc, *dh32, *logits;
   __half *dxn, *datt, *dh, *kcache, *vcache;
   long cache_row_stride, cache_layer_stride;
   CrossAttnWorkspace xws;
@@ -168,6 +171,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     WL_CUDA(cudaEventCreate(&c->ev1));
     gemm_prime();
     attention_prime();
+    flash_attn_prime();
     c->enc.resize(c->Le);
     c->dec.resize(c->Ld);
     for (int i = c->NS - 1; i >= 0; --i) c->slot_free.push_back(i);
@@ -386,6 +390,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->dx = dalloc<float>(c, R * d);
   c->dqkv = dalloc<float>(c, R * 3 * d);
   c->dqc = dalloc<float>(c, R * d);
+  c->dh32 = dalloc<float>(c, R * ff);
   c->logits = dalloc<float>(c, R * c->Vld);
   c->dxn = dalloc<__half>(c, Rp * d);
   c->datt = dalloc<__half>(c, Rp * d);
@@ -508,7 +513,9 @@ static void encoder_pass(wl_ctx* c, int nb, const int* slots_host, const float* 
       e.out = c->vt; e.ldm = S_PAD; e.ldn = 1; e.ob1 = (long)d * S_PAD; e.bias = L.b_v; e.bias_on_m = 1;
       gemm_tn(st, opnd(L.w_v, d, d, d), opnd(c->xn, S_ENC, d, d, nb, (long)S_ENC * d), d, S_ENC, d, e);
     }
-    for (int b0 = 0; b0 < nb; b0 += c->AB) {
+    static const bool fused_attn = [] { const char* e = getenv("WLB200_FUSED_ATTN"); return e ? atoi(e) != 0 : true; }();
+    if (fused_attn) encoder_attention_fused(st, c->qk, c->vt, c->attn, nb, H, d);
+    else for (int b0 = 0; b0 < nb; b0 += c->AB) {
       const int ab = std::min(c->AB, nb - b0);
       const __half* qb = c->qk + (long)b0 * S_ENC * 2 * d;
       {
@@ -644,49 +651,43 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     e.bias_on_m = 1;
     gemm_tn(st, opnd(W, n_out, K, K), opnd(X, R, K, K), n_out, R, K, e);
   };
+  static const bool splitk = [] { const char* e = getenv("WLB200_SPLITK"); return e ? atoi(e) != 0 : true; }();
+  // Decode GEMMs are weight-streaming (M = out features, N = rows): split K over all SMs and let the partial
+  // sums accumulate atomically into fp32 buffers that already hold the residual (x) or zeros (cleared by the
+  // preceding LayerNorm launch).
+  auto acc_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* out, int ldn, const float* bias) {
+    GemmEpilogue e;
+    e.out = out; e.out_f32 = 1; e.ldn = ldn; e.bias = bias;
+    if (splitk) e.accumulate = 1;
+    else if (out == c->dx) { e.resid = c->dx; e.rldm = 1; e.rldn = ldn; }
+    swap_gemm(W, n_out, K, X, e);
+  };
   for (int l = 0; l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d);
-    {
-      GemmEpilogue e;
-      e.out = c->dqkv; e.out_f32 = 1; e.ldn = 3 * d; e.bias = L.b_qkv;
-      swap_gemm(L.w_qkv, 3 * d, d, c->dxn, e);
-    }
+    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d, splitk ? c->dqkv : nullptr, (long)R * 3 * d);
+    acc_gemm(L.w_qkv, 3 * d, d, c->dxn, c->dqkv, 3 * d, L.b_qkv);
     decoder_self_attn(st, s, c->dqkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
-    {
-      GemmEpilogue e;
-      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_o; e.resid = c->dx; e.rldm = 1; e.rldn = d;
-      swap_gemm(L.w_o, d, d, c->datt, e);
-    }
-    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d);
-    {
-      GemmEpilogue e;
-      e.out = c->dqc; e.out_f32 = 1; e.ldn = d; e.bias = L.b_qc;
-      swap_gemm(L.w_qc, d, d, c->dxn, e);
-    }
+    acc_gemm(L.w_o, d, d, c->datt, c->dx, d, L.b_o);
+    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d, splitk ? c->dqc : nullptr, (long)R * d);
+    acc_gemm(L.w_qc, d, d, c->dxn, c->dqc, d, L.b_qc);
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
     decoder_cross_attn(st, s, c->dqc, c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz, c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz,
                        slot_sz, ws, c->datt, B, Kr, H, d, nsplit);
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
-    {
-      GemmEpilogue e;
-      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_oc; e.resid = c->dx; e.rldm = 1; e.rldn = d;
-      swap_gemm(L.w_oc, d, d, c->datt, e);
-    }
-    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d);
-    {
+    acc_gemm(L.w_oc, d, d, c->datt, c->dx, d, L.b_oc);
+    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d, splitk ? c->dh32 : nullptr, (long)R * ff);
+    if (splitk) {
+      acc_gemm(L.w_fc1, ff, d, c->dxn, c->dh32, ff, L.b_fc1);
+      gelu_cast(st, c->dh32, c->dh, (long)R * ff);
+    } else {
       GemmEpilogue e;
       e.out = c->dh; e.out_f32 = 0; e.ldn = ff; e.bias = L.b_fc1; e.gelu = 1;
       swap_gemm(L.w_fc1, ff, d, c->dxn, e);
     }
-    {
-      GemmEpilogue e;
-      e.out = c->dx; e.out_f32 = 1; e.ldn = d; e.bias = L.b_fc2; e.resid = c->dx; e.rldm = 1; e.rldn = d;
-      swap_gemm(L.w_fc2, d, ff, c->dh, e);
-    }
+    acc_gemm(L.w_fc2, d, ff, c->dh, c->dx, d, L.b_fc2);
   }
   layernorm_rows(st, c->dx, c->lnf_g, c->lnf_b, c->dxn, nullptr, R, d);
   {

@@ -1,0 +1,260 @@
+// K5 (v2): fused encoder self-attention on tcgen05 -- scores never leave the SM.
+//   one CTA = 128 queries of one (stream, head); loop over 12 key tiles of 128:
+//     S = Q K^T            tcgen05.mma 128x128x16 x4  -> TMEM (double buffered)
+//     online softmax       4 warps, thread = query row: tcgen05.ld S, exp2, write P (fp16) into smem in the
+//                          128B-swizzled K-major layout the tensor core reads
+//     O_blk = P V          tcgen05.mma 128x64x16 x8   -> TMEM; accumulated into registers with the lazy rescale
+//   warp 0: TMA producer (Q once, K / V^T tiles through a 3-stage mbarrier ring), warp 1: MMA issuer,
+//   warp 2: TMEM allocator, warps 4-7: softmax + output.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace wl {
+
+constexpr int FA_BQ = 128, FA_BK = 128, FA_STAGES = 3;
+constexpr int FA_Q_BYTES = FA_BQ * 128;              // 128 rows x 64 halves
+constexpr int FA_K_BYTES = FA_BK * 128;              // 128 keys x 64 halves
+constexpr int FA_V_BYTES = 2 * 64 * 128;             // two k-blocks of [64 dd][64 keys]
+constexpr int FA_P_BYTES = 2 * FA_BQ * 128;          // two k-blocks of [128 rows][64 keys]
+constexpr int FA_STAGE_BYTES = FA_K_BYTES + FA_V_BYTES;
+constexpr int FA_SMEM = 1024 + FA_Q_BYTES + FA_STAGES * FA_STAGE_BYTES + FA_P_BYTES + 256;
+constexpr int FA_NT = (S_ENC + FA_BK - 1) / FA_BK;   // 12 key tiles
+
+struct FaParams {
+  int q_pos[3], k_pos[3], v_pos[3];
+  __half* out;   // [B*1500][d]
+  int d;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ void fa_coords(int (&c)[4], const int (&pos)[3], int k0, int row, int i1, int i2) {
+  c[0] = k0; c[1] = c[2] = c[3] = 0;
+  c[pos[0]] = row; c[pos[1]] = i1; c[pos[2]] = i2;
+}
+
+__global__ void __launch_bounds__(256, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t fa_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = base;
+  uint8_t* sKV = sQ + FA_Q_BYTES;
+  uint8_t* sP = sKV + FA_STAGES * FA_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                 // [FA_STAGES]
+  uint64_t* kv_empty = kv_full + FA_STAGES;     // [FA_STAGES]
+  uint64_t* s_full = kv_empty + FA_STAGES;      // [2]
+  uint64_t* s_empty = s_full + 2;               // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* o_full = p_full + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S[2] = {tmem, tmem + 128};
+  const uint32_t tmem_O = tmem + 256;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int c[4];
+      mbar_expect_tx(q_full, FA_Q_BYTES);
+      fa_coords(c, p.q_pos, 0, qt * FA_BQ, h, b);
+      tma_load_4d(sQ, &tmQ, q_full, c[0], c[1], c[2], c[3]);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < FA_NT; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = sKV + stage * FA_STAGE_BYTES;
+        mbar_expect_tx(&kv_full[stage], FA_STAGE_BYTES);
+        fa_coords(c, p.k_pos, 0, j * FA_BK, h, b);
+        tma_load_4d(sk, &tmK, &kv_full[stage], c[0], c[1], c[2], c[3]);
+        fa_coords(c, p.v_pos, j * FA_BK, 0, h, b);
+        tma_load_4d(sk + FA_K_BYTES, &tmV, &kv_full[stage], c[0], c[1], c[2], c[3]);
+        fa_coords(c, p.v_pos, j * FA_BK + 64, 0, h, b);
+        tma_load_4d(sk + FA_K_BYTES + 64 * 128, &tmV, &kv_full[stage], c[0], c[1], c[2], c[3]);
+        if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(FA_BQ, FA_BK);
+      constexpr uint32_t idesc_o = umma_idesc_f16(FA_BQ, 64);
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+      auto issue_pv = [&](int i) {
+        const int st = i % FA_STAGES;
+        mbar_wait(p_full, i & 1);                 // P_i written by the softmax warps
+        mbar_wait(o_empty, (i & 1) ^ 1);          // O_blk of tile i-1 consumed
+        tc_fence_after();
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * FA_STAGE_BYTES + FA_K_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a = pdesc + (uint64_t)((kk >> 2) * (FA_BQ * 128 >> 4) + (kk & 3) * 2);
+          const uint64_t bd = vdesc + (uint64_t)((kk >> 2) * (64 * 128 >> 4) + (kk & 3) * 2);
+          umma_f16(tmem_O, a, bd, idesc_o, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < FA_NT; ++j) {
+        const int st = j % FA_STAGES;
+        mbar_wait(&kv_full[st], (j / FA_STAGES) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * FA_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_S[j & 1], qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+        if (j >= 1) issue_pv(j - 1);
+      }
+      issue_pv(FA_NT - 1);
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp & 3, lane = lane_id();
+    const int row = q4 * 32 + lane;                       // query row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const int qrow = qt * FA_BQ + row;
+    float m = -INFINITY, l = 0.f, m_ref = -INFINITY;
+    float o[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) o[e] = 0.f;
+    auto accumulate_o = [&](int i, float m_i) {
+      // O += PV_i, where PV_i was formed with probabilities relative to m_i
+      mbar_wait(o_full, i & 1);
+      tc_fence_after();
+      const float resc = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_i);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c0 + e] = fmaf(o[c0 + e], resc, __uint_as_float(v[e]));
+      }
+      m_ref = m_i;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    };
+    float m_prev_tile = -INFINITY;
+    for (int j = 0; j < FA_NT; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const int key0 = j * FA_BK;
+      // pass 1: row max of the scaled scores
+      float mx = m;
+#pragma unroll
+      for (int c0 = 0; c0 < FA_BK; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S[j & 1] + lane_off + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (key0 + c0 + e < S_ENC) mx = fmaxf(mx, __uint_as_float(v[e]) * p.scale_log2);
+      }
+      const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - mx);
+      // the P buffer (and O_blk) of the previous tile must have been consumed by its PV MMA
+      if (j >= 1) accumulate_o(j - 1, m_prev_tile);
+      // pass 2: probabilities -> smem (swizzled), row sum
+      float sum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < FA_BK; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S[j & 1] + lane_off + c0, v);
+        tmem_ld_wait();
+        uint8_t* prow = sP + (c0 >> 6) * (FA_BQ * 128) + row * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {           // 4 chunks of 8 keys = 16 bytes
+          __align__(16) __half2 h2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kidx = c0 + g * 8 + 2 * e;
+            float p0 = (key0 + kidx < S_ENC) ? exp2f(__uint_as_float(v[g * 8 + 2 * e]) * p.scale_log2 - mx) : 0.f;
+            float p1 = (key0 + kidx + 1 < S_ENC) ? exp2f(__uint_as_float(v[g * 8 + 2 * e + 1]) * p.scale_log2 - mx) : 0.f;
+            h2[e] = __floats2half2_rn(p0, p1);
+            // sum what the tensor core will actually see (fp16-rounded), like a materialised fp16 P would
+            const float2 r = __half22float2(h2[e]);
+            sum += r.x + r.y;
+          }
+          const int chunk = ((c0 & 63) >> 3) + g;            // 16-byte chunk inside the 128-byte row
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
+        }
+      }
+      l = l * alpha + sum;
+      m = mx;
+      m_prev_tile = mx;
+      tc_fence_before();
+      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[j & 1]);
+        mbar_arrive(p_full);
+      }
+    }
+    accumulate_o(FA_NT - 1, m_prev_tile);
+    if (qrow < S_ENC) {
+      const float inv = 1.f / l;
+      __half* dst = p.out + ((long)b * S_ENC + qrow) * p.d + h * 64;
+#pragma unroll
+      for (int e = 0; e < 64; e += 8) {
+        __align__(16) __half2 h2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(o[e + 2 * t] * inv, o[e + 2 * t + 1] * inv);
+        *reinterpret_cast<uint4*>(dst + e) = *reinterpret_cast<const uint4*>(h2);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+void flash_attn_prime() {
+  WL_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+}
+
+// qk: [nb][1500][2d] fp16 (q | k), vt: [nb][d][S_PAD] fp16 (V transposed per head), out: [nb*1500][d] fp16
+void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt, __half* out, int nb, int H, int d) {
+  GemmOperand q, k, v;
+  q.ptr = qk; q.rows = S_ENC; q.k = 64; q.ld = 2L * d; q.n1 = H; q.s1 = 64; q.n2 = nb; q.s2 = (long)S_ENC * 2 * d;
+  k = q;
+  k.ptr = qk + d;
+  v.ptr = vt; v.rows = 64; v.k = S_PAD; v.ld = S_PAD; v.n1 = H; v.s1 = 64L * S_PAD; v.n2 = nb; v.s2 = (long)d * S_PAD;
+  const TmapInfo iq = make_tmap(q, FA_BQ), ik = make_tmap(k, FA_BK), iv = make_tmap(v, 64);
+  FaParams p;
+  for (int i = 0; i < 3; ++i) { p.q_pos[i] = iq.pos[i]; p.k_pos[i] = ik.pos[i]; p.v_pos[i] = iv.pos[i]; }
+  p.out = out; p.d = d;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid(FA_NT, H, nb);
+  flash_attn_kernel<<<grid, 256, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
+}  // namespace wl

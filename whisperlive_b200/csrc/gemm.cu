@@ -25,6 +25,8 @@ struct GemmKParams {
   int a_pos[3], b_pos[3];  // tensor-map coordinate slots (1..3) of (row, i1, i2)
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
+  int accum;        // 1: grid z enumerates K ranges; partial sums are atomically added to the fp32 output
+  int kb_per_split; // k-blocks per split (accum mode)
 };
 
 constexpr int BM = 128;
@@ -32,9 +34,24 @@ constexpr int BK = 64;  // 64 halves = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 template <int cnt>
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2) {
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2,
+                                               int split = 0) {
   const GemmEpilogue& e = p.e;
   if (m >= p.M) return;
+  if (p.accum) {
+    // split-K: out (fp32, already holding the residual or zeros) += partial (+ bias from split 0)
+    const long ob = m * e.ldm;
+    const float bm0 = (split == 0 && e.bias && e.bias_on_m) ? e.bias[m] : 0.f;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const int n = n0 + i;
+      if (n >= p.N) break;
+      float x = __uint_as_float(v[i]) + bm0;
+      if (split == 0 && e.bias && !e.bias_on_m) x += e.bias[n];
+      atomicAdd((float*)e.out + ob + (long)n * e.ldn, x);
+    }
+    return;
+  }
   if constexpr (cnt >= 8) if (e.mode == GEMM_HEADSPLIT) {
     // m = (b, s), n = (h, dd); one thread writes cnt (<=32) consecutive dd of one head row
     const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
@@ -126,9 +143,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int z = p.accum ? 0 : blockIdx.z, split = p.accum ? blockIdx.z : 0;
   const int i1 = z % p.zn1, i2 = z / p.zn1;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb0 = p.accum ? split * p.kb_per_split : 0;
+  const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;  // host guarantees >= 1
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -163,7 +183,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-        ca[0] = cb[0] = kb * BK;
+        ca[0] = cb[0] = (kb0 + kb) * BK;
         tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], ca[0], ca[1], ca[2], ca[3]);
         tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], cb[0], cb[1], cb[2], cb[3]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -201,13 +221,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld_32x32(lane_addr + c, v);
         tmem_ld_wait();
-        epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2);
+        epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
       }
     } else {
       uint32_t v[16];
       tmem_ld_32x16(lane_addr, v);
       tmem_ld_wait();
-      epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2);
+      epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2, split);
     }
   }
   tc_fence_before();
@@ -236,25 +256,23 @@ static EncodeTiledFn encode_fn() {
 struct TmapKey {
   const void* ptr;
   long rows, k, ld, s1, s2;
-  int n1, n2, box_rows;
+  int n1, n2, box_rows, box_k;
   bool operator<(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) < 0; }
 };
 
 // Tensor map + where the (row, i1, i2) coordinates sit among its dims 1..3.  TMA wants strides in
 // ascending order (each a multiple of the previous), so the view's dims are sorted by stride: e.g. the
 // per-head Q/K operand of attention is {k, head (128 B), row (2*ld B), batch}.
-struct TmapInfo {
-  CUtensorMap tm;
-  int pos[3];
-};
+static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k = BK);
+TmapInfo make_tmap(const GemmOperand& op, int box_rows, int box_k) { return get_tmap(op, box_rows, box_k); }
 
-static TmapInfo get_tmap(const GemmOperand& op, int box_rows) {
+static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
   static std::map<TmapKey, TmapInfo> cache;
   static std::mutex mu;
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = op.ptr; key.rows = op.rows; key.k = op.k; key.ld = op.ld; key.s1 = op.s1; key.s2 = op.s2;
-  key.n1 = op.n1; key.n2 = op.n2; key.box_rows = box_rows;
+  key.n1 = op.n1; key.n2 = op.n2; key.box_rows = box_rows; key.box_k = box_k;
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -272,7 +290,7 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows) {
   TmapInfo info;
   cuuint64_t dims[4] = {(cuuint64_t)op.k, 1, 1, 1};
   cuuint64_t strides[3];
-  cuuint32_t box[4] = {(cuuint32_t)BK, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_k, 1, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 3; ++i) {
     WL_CHECK(order[i].stride > 0 && (order[i].stride * 2) % 16 == 0, WL_ERR_ARG,
@@ -316,6 +334,8 @@ void gemm_prime() {
   prime_cfg<64, 4, 2>();
   prime_cfg<128, 3, 2>();
   prime_cfg<256, 4, 1>();
+  prime_cfg<64, 8, 1>();
+  prime_cfg<128, 6, 1>();
 }
 
 static int env_int(const char* name, int dflt) {
@@ -336,6 +356,8 @@ static GemmKParams make_params(const GemmOperand& A, const GemmOperand& B, int M
   *Z = za > zb ? za : zb;
   p.e = epi;
   p.vec_ok = 0;
+  p.accum = 0;
+  p.kb_per_split = 0;
   if (epi.mode == GEMM_STORE && epi.ldn == 1) {
     const int a = epi.out_f32 ? 4 : 8;  // elements per 16 bytes
     bool ok = ((uintptr_t)epi.out & 15) == 0 && epi.ldm % 8 == 0 && epi.ob1 % 8 == 0 && epi.ob2 % 8 == 0 && N % 8 == 0;
@@ -363,8 +385,21 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   else if (N <= 16) bn = 16;
   else if (N <= 32) bn = 32;
   else if (N <= 64) bn = 64;
+  else if (N % 256 == 0 && M >= 1024 && epi.ldn == 1 && epi.mode == GEMM_STORE) bn = 256;
   else bn = 128;
   if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
+  const bool skinny = epi.ldm == 1 && epi.mode == GEMM_STORE;  // swap-AB decode GEMM: few tiles, deep pipeline
+  if (epi.accumulate) {
+    WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && epi.mode == GEMM_STORE, WL_ERR_ARG,
+             "gemm_tn: accumulate (split-K) needs a plain fp32 output");
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int tiles = cdiv(N, bn) * cdiv(M, BM), total_kb = cdiv(K, BK);
+    int splits = tiles >= sms ? 1 : std::min(total_kb, std::max(1, sms / tiles));
+    p.accum = 1;
+    p.kb_per_split = cdiv(total_kb, splits);
+    Z = cdiv(total_kb, p.kb_per_split);
+  }
   const TmapInfo ia = get_tmap(A, BM), ib = get_tmap(B, bn);
   const CUtensorMap& ta = ia.tm;
   const CUtensorMap& tb = ib.tm;
@@ -372,8 +407,14 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   switch (bn) {
     case 16: launch_cfg<16, 8, 1>(stream, ta, tb, p, Z); break;
     case 32: launch_cfg<32, 8, 1>(stream, ta, tb, p, Z); break;
-    case 64: launch_cfg<64, 4, 2>(stream, ta, tb, p, Z); break;
-    case 128: launch_cfg<128, 3, 2>(stream, ta, tb, p, Z); break;
+    case 64:
+      if (skinny) launch_cfg<64, 8, 1>(stream, ta, tb, p, Z);
+      else launch_cfg<64, 4, 2>(stream, ta, tb, p, Z);
+      break;
+    case 128:
+      if (skinny) launch_cfg<128, 6, 1>(stream, ta, tb, p, Z);
+      else launch_cfg<128, 3, 2>(stream, ta, tb, p, Z);
+      break;
     case 256: launch_cfg<256, 4, 1>(stream, ta, tb, p, Z); break;
     default: WL_CHECK(false, WL_ERR_ARG, "unsupported BN %d", bn);
   }
@@ -393,6 +434,12 @@ __global__ void gemm_tn_simt_kernel(GemmOperand A, GemmOperand B, GemmKParams p)
   const int kk = ka < kb ? ka : kb;
   for (int k = 0; k < kk; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
   uint32_t v[1] = {__float_as_uint(acc)};
+  if (p.e.accumulate) {  // same contract as the split-K path, single pass
+    float x = acc;
+    if (p.e.bias) x += p.e.bias[p.e.bias_on_m ? m : n];
+    ((float*)p.e.out)[m * p.e.ldm + n * p.e.ldn] += x;
+    return;
+  }
   GemmKParams q = p;
   q.vec_ok = 0;
   if (q.e.mode == GEMM_HEADSPLIT) {

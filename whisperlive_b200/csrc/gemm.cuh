@@ -33,6 +33,7 @@ struct GemmEpilogue {
   int gelu = 0;              // exact erf GELU after bias
   const float* resid = nullptr;  // fp32 residual added last; same indexing scheme as out
   long rldm = 0, rldn = 1, rb1 = 0, rb2 = 0;
+  int accumulate = 0;        // split-K: out (fp32, pre-initialised) += A*B^T (+bias); atomics, order not deterministic
   int mode = GEMM_STORE;
   // GEMM_HEADSPLIT parameters
   int hs_S = 0, hs_H = 0;
@@ -50,5 +51,12 @@ void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& 
                   const GemmEpilogue& epi);
 
 long gemm_launch_count();
+
+// Tensor map over an operand view (dims sorted by stride) + the coordinate slots of (row, i1, i2).
+struct TmapInfo {
+  CUtensorMap tm;
+  int pos[3];
+};
+TmapInfo make_tmap(const GemmOperand& op, int box_rows, int box_k = 64);
 
 }  // namespace wl

@@ -27,7 +27,9 @@ void mel_forward(cudaStream_t st, const float* pcm, const long* pcm_off, float* 
 void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int n_mels);
 // y = LayerNorm(x) * gamma + beta ; x f32 [rows][d] -> y fp16 [rows][d] (and optionally f32 copy)
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32,
-                    long rows, int d);
+                    long rows, int d, float* zero_buf = nullptr, long zero_n = 0);
+// out = fp16(gelu(in)), n elements (n % 4 == 0)
+void gelu_cast(cudaStream_t st, const float* in, __half* out, long n);
 // scores f32 [rows][ld_in] (first n valid) -> softmax(scale * s) as fp16 [rows][ld_out], columns >= n zeroed
 void softmax_rows(cudaStream_t st, const float* s, __half* p, long rows, int n, int ld_in, int ld_out, float scale);
 
