@@ -36,6 +36,7 @@ struct DecLayer {
 
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
+  long kernels = 0;  // kernel nodes per replay
 };
 
 struct wl_ctx {
@@ -51,7 +52,8 @@ struct wl_ctx {
   std::vector<void*> allocs;
   std::map<std::string, void*> dev;                 // raw uploaded tensors (fp16 for ndim>=2, f32 for 1-D)
   std::map<std::string, std::vector<int64_t>> shape;
-  long launches = 0;
+  long graph_launched = 0;   // kernels executed through graph replays
+  long capture_counted = 0;  // launcher calls that were captured, not executed
 
   // weights
   __half *w_conv1 = nullptr, *w_conv2 = nullptr, *emb = nullptr, *pos_dec = nullptr;
@@ -201,7 +203,9 @@ extern "C" void wl_destroy(wl_ctx* c) {
 }
 
 extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
-extern "C" int64_t wl_kernel_launches(wl_ctx* c) { return c ? gemm_launch_count() + other_launch_count() : 0; }
+extern "C" int64_t wl_kernel_launches(wl_ctx* c) {
+  return c ? gemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
+}
 extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) { return (c && which >= 0 && which < 3) ? c->last_ms[which] : -1.f; }
 
 // ------------------------------------------------------------------------------------------ weights
@@ -664,12 +668,12 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   };
   for (int l = 0; l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d, splitk ? c->dqkv : nullptr, (long)R * 3 * d);
+    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d, splitk ? c->dqkv : nullptr, splitk ? (long)R * 3 * d : 0);
     acc_gemm(L.w_qkv, 3 * d, d, c->dxn, c->dqkv, 3 * d, L.b_qkv);
     decoder_self_attn(st, s, c->dqkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
     acc_gemm(L.w_o, d, d, c->datt, c->dx, d, L.b_o);
-    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d, splitk ? c->dqc : nullptr, (long)R * d);
+    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d, splitk ? c->dqc : nullptr, splitk ? (long)R * d : 0);
     acc_gemm(L.w_qc, d, d, c->dxn, c->dqc, d, L.b_qc);
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
@@ -678,7 +682,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
     acc_gemm(L.w_oc, d, d, c->datt, c->dx, d, L.b_oc);
-    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d, splitk ? c->dh32 : nullptr, (long)R * ff);
+    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d, splitk ? c->dh32 : nullptr, splitk ? (long)R * ff : 0);
     if (splitk) {
       acc_gemm(L.w_fc1, ff, d, c->dxn, c->dh32, ff, L.b_fc1);
       gelu_cast(st, c->dh32, c->dh, (long)R * ff);
@@ -791,6 +795,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms);
 
   cudaGraphExec_t exec = nullptr;
+  long graph_kernels = 0;
   if (o->use_cuda_graph) {
     char key[160];
     snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x/%u", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
@@ -798,6 +803,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
       cudaGraph_t g;
+      const long before = gemm_launch_count() + other_launch_count();
       WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       try {
         decode_step(c, B, Kr, so, vi, nsplit, false);
@@ -806,10 +812,13 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
         throw;
       }
       WL_CUDA(cudaStreamEndCapture(st, &g));
+      ge.kernels = gemm_launch_count() + other_launch_count() - before;
+      c->capture_counted += ge.kernels;
       WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
       cudaGraphDestroy(g);
     }
     exec = ge.exec;
+    graph_kernels = ge.kernels;
   }
   ensure_host(c, (size_t)B * (T_MAX + 8) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
   int* h_done = c->h_int;  // reuse (prompts are already on the device: the copies above are stream-ordered)
@@ -819,8 +828,12 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   while (ran < max_steps) {
     const int n = std::min(check_every, max_steps - ran);
     for (int i = 0; i < n; ++i) {
-      if (exec) WL_CUDA(cudaGraphLaunch(exec, st));
-      else decode_step(c, B, Kr, so, vi, nsplit, false);
+      if (exec) {
+        WL_CUDA(cudaGraphLaunch(exec, st));
+        c->graph_launched += graph_kernels;
+      } else {
+        decode_step(c, B, Kr, so, vi, nsplit, false);
+      }
     }
     ran += n;
     WL_CUDA(cudaMemcpyAsync(h_done, c->ds.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));

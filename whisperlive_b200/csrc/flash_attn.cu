@@ -5,7 +5,7 @@
 //                          128B-swizzled K-major layout the tensor core reads
 //     O_blk = P V          tcgen05.mma 128x64x16 x8   -> TMEM; accumulated into registers with the lazy rescale
 //   warp 0: TMA producer (Q once, K / V^T tiles through a 3-stage mbarrier ring), warp 1: MMA issuer,
-//   warp 2: TMEM allocator, warps 4-7: softmax + output.
+//   warp 2: TMEM allocator, warps 4-11: softmax + output (two threads per query row, 64 keys each).
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -27,12 +27,19 @@ struct FaParams {
   float scale_log2;  // softmax scale * log2(e)
 };
 
+__device__ __forceinline__ float fa_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
 __device__ __forceinline__ void fa_coords(int (&c)[4], const int (&pos)[3], int k0, int row, int i1, int i2) {
   c[0] = k0; c[1] = c[2] = c[3] = 0;
   c[pos[0]] = row; c[pos[1]] = i1; c[pos[2]] = i2;
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t fa_raw[];
@@ -50,6 +57,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* o_full = p_full + 1;
   uint64_t* o_empty = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  __shared__ float smax[2][2][FA_BQ];   // [tile parity][column half][row]: per-tile row-max exchange
 
   const int warp = threadIdx.x >> 5;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -62,10 +70,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 1 && elect_one()) {
     mbar_init(q_full, 1);
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -136,27 +144,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       issue_pv(FA_NT - 1);
     }
   } else if (warp >= 4) {
-    const int q4 = warp & 3, lane = lane_id();
+    // 8 softmax warps = 2 per SM sub-partition.  Warps 4-7 own key columns [0,64) of the tile and output
+    // columns [0,32); warps 8-11 own keys [64,128) and outputs [32,64).  Thread pair (w, w+4) shares a query row.
+    const int q4 = warp & 3, half = (warp - 4) >> 2, lane = lane_id();
     const int row = q4 * 32 + lane;                       // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const int qrow = qt * FA_BQ + row;
-    float m = -INFINITY, l = 0.f, m_ref = -INFINITY;
-    float o[64];
+    float m = -INFINITY, l = 0.f, m_ref = -INFINITY;      // m, m_ref in the scaled log2 domain
+    float o[32];
 #pragma unroll
-    for (int e = 0; e < 64; ++e) o[e] = 0.f;
+    for (int e = 0; e < 32; ++e) o[e] = 0.f;
     auto accumulate_o = [&](int i, float m_i) {
       // O += PV_i, where PV_i was formed with probabilities relative to m_i
       mbar_wait(o_full, i & 1);
       tc_fence_after();
-      const float resc = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_i);
+      const float resc = (m_ref == -INFINITY) ? 0.f : fa_exp2(m_ref - m_i);
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_O + lane_off + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c0 + e] = fmaf(o[c0 + e], resc, __uint_as_float(v[e]));
-      }
+      for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], resc, __uint_as_float(v[e]));
       m_ref = m_i;
       tc_fence_before();
       __syncwarp();
@@ -166,43 +173,56 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int j = 0; j < FA_NT; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const int key0 = j * FA_BK;
-      // pass 1: row max of the scaled scores
-      float mx = m;
+      const int key0 = j * FA_BK + half * 64;
+      const int nvalid = S_ENC - key0;                    // keys of this half that exist (only the last tile is ragged)
+      const uint32_t s_addr = tmem_S[j & 1] + lane_off + half * 64;
+      // pass 1: raw row max over this thread's 64 keys
+      float mx_raw = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < FA_BK; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_S[j & 1] + lane_off + c0, v);
+        tmem_ld_32x32(s_addr + c0, v);
         tmem_ld_wait();
+        if (nvalid >= c0 + 32) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (key0 + c0 + e < S_ENC) mx = fmaxf(mx, __uint_as_float(v[e]) * p.scale_log2);
+          for (int e = 0; e < 32; ++e) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < nvalid) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
+        }
       }
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - mx);
+      smax[j & 1][half][row] = mx_raw;
+      softmax_sync();                                     // both halves of every row have published their max
+      const float mx = fmaxf(m, fmaxf(mx_raw, smax[j & 1][half ^ 1][row]) * p.scale_log2);
+      const float alpha = (m == -INFINITY) ? 0.f : fa_exp2(m - mx);
       // the P buffer (and O_blk) of the previous tile must have been consumed by its PV MMA
       if (j >= 1) accumulate_o(j - 1, m_prev_tile);
       // pass 2: probabilities -> smem (swizzled), row sum
       float sum = 0.f;
+      uint8_t* prow = sP + half * (FA_BQ * 128) + row * 128;
 #pragma unroll
-      for (int c0 = 0; c0 < FA_BK; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_S[j & 1] + lane_off + c0, v);
+        tmem_ld_32x32(s_addr + c0, v);
         tmem_ld_wait();
-        uint8_t* prow = sP + (c0 >> 6) * (FA_BQ * 128) + row * 128;
+        const bool full = nvalid >= c0 + 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {           // 4 chunks of 8 keys = 16 bytes
+        for (int g = 0; g < 4; ++g) {                     // 4 chunks of 8 keys = 16 bytes
           __align__(16) __half2 h2[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int kidx = c0 + g * 8 + 2 * e;
-            float p0 = (key0 + kidx < S_ENC) ? exp2f(__uint_as_float(v[g * 8 + 2 * e]) * p.scale_log2 - mx) : 0.f;
-            float p1 = (key0 + kidx + 1 < S_ENC) ? exp2f(__uint_as_float(v[g * 8 + 2 * e + 1]) * p.scale_log2 - mx) : 0.f;
+            const int kk = c0 + g * 8 + 2 * e;
+            float p0 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, -mx));
+            float p1 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, -mx));
+            if (!full) {
+              if (kk >= nvalid) p0 = 0.f;
+              if (kk + 1 >= nvalid) p1 = 0.f;
+            }
+            sum += p0 + p1;
             h2[e] = __floats2half2_rn(p0, p1);
-            // sum what the tensor core will actually see (fp16-rounded), like a materialised fp16 P would
-            const float2 r = __half22float2(h2[e]);
-            sum += r.x + r.y;
           }
-          const int chunk = ((c0 & 63) >> 3) + g;            // 16-byte chunk inside the 128-byte row
+          const int chunk = (c0 >> 3) + g;                // 16-byte chunk inside the 128-byte row
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
         }
       }
@@ -218,11 +238,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
     accumulate_o(FA_NT - 1, m_prev_tile);
+    // total row sum = sum of the two halves (same running max in both)
+    smax[0][half][row] = l;
+    softmax_sync();
+    const float inv = 1.f / (l + smax[0][half ^ 1][row]);
     if (qrow < S_ENC) {
-      const float inv = 1.f / l;
-      __half* dst = p.out + ((long)b * S_ENC + qrow) * p.d + h * 64;
+      __half* dst = p.out + ((long)b * S_ENC + qrow) * p.d + h * 64 + half * 32;
 #pragma unroll
-      for (int e = 0; e < 64; e += 8) {
+      for (int e = 0; e < 32; e += 8) {
         __align__(16) __half2 h2[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(o[e + 2 * t] * inv, o[e + 2 * t + 1] * inv);
@@ -252,7 +275,7 @@ void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt
   p.out = out; p.d = d;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid(FA_NT, H, nb);
-  flash_attn_kernel<<<grid, 256, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
+  flash_attn_kernel<<<grid, 384, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

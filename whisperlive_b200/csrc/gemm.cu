@@ -45,10 +45,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
 #pragma unroll
     for (int i = 0; i < cnt; ++i) {
       const int n = n0 + i;
-      if (n >= p.N) break;
-      float x = __uint_as_float(v[i]) + bm0;
-      if (split == 0 && e.bias && !e.bias_on_m) x += e.bias[n];
-      atomicAdd((float*)e.out + ob + (long)n * e.ldn, x);
+      if (n < p.N) {
+        float x = __uint_as_float(v[i]) + bm0;
+        if (split == 0 && e.bias && !e.bias_on_m) x += e.bias[n];
+        atomicAdd((float*)e.out + ob + (long)n * e.ldn, x);
+      }
     }
     return;
   }
@@ -82,6 +83,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
     for (int i = 0; i < cnt; i += 8) {
       const int n = n0 + i;
       if (n >= p.N) break;
+      if (n + 8 > p.N) {  // ragged tail of the last tile: element-wise
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (n + j < p.N) {
+            float x1 = __uint_as_float(v[i + j]) + bm;
+            if (e.bias && !e.bias_on_m) x1 += e.bias[n + j];
+            if (e.gelu) x1 = gelu_erf(x1);
+            if (e.resid) x1 += e.resid[rbase + n + j];
+            if (e.out_f32) ((float*)e.out)[obase + n + j] = x1;
+            else ((__half*)e.out)[obase + n + j] = __float2half_rn(x1);
+          }
+        }
+        continue;
+      }
       float x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[i + j]) + bm;
@@ -177,15 +192,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
       const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
-      int ca[4] = {0, 0, 0, 0}, cb[4] = {0, 0, 0, 0};
-      ca[p.a_pos[0]] = tile_m * BM; ca[p.a_pos[1]] = a1; ca[p.a_pos[2]] = a2;
-      cb[p.b_pos[0]] = tile_n * BN; cb[p.b_pos[1]] = b1; cb[p.b_pos[2]] = b2;
+      // coordinate slot s (1..3) of a tensor map holds whichever of (row, i1, i2) was sorted there
+      auto slot = [](const int (&pos)[3], int s, int row, int j1, int j2) {
+        return pos[0] == s ? row : (pos[1] == s ? j1 : (pos[2] == s ? j2 : 0));
+      };
+      const int ca1 = slot(p.a_pos, 1, tile_m * BM, a1, a2), ca2 = slot(p.a_pos, 2, tile_m * BM, a1, a2),
+                ca3 = slot(p.a_pos, 3, tile_m * BM, a1, a2);
+      const int cb1 = slot(p.b_pos, 1, tile_n * BN, b1, b2), cb2 = slot(p.b_pos, 2, tile_n * BN, b1, b2),
+                cb3 = slot(p.b_pos, 3, tile_n * BN, b1, b2);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-        ca[0] = cb[0] = (kb0 + kb) * BK;
-        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], ca[0], ca[1], ca[2], ca[3]);
-        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], cb[0], cb[1], cb[2], cb[3]);
+        const int k0 = (kb0 + kb) * BK;
+        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], k0, ca1, ca2, ca3);
+        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -360,7 +380,7 @@ static GemmKParams make_params(const GemmOperand& A, const GemmOperand& B, int M
   p.kb_per_split = 0;
   if (epi.mode == GEMM_STORE && epi.ldn == 1) {
     const int a = epi.out_f32 ? 4 : 8;  // elements per 16 bytes
-    bool ok = ((uintptr_t)epi.out & 15) == 0 && epi.ldm % 8 == 0 && epi.ob1 % 8 == 0 && epi.ob2 % 8 == 0 && N % 8 == 0;
+    bool ok = ((uintptr_t)epi.out & 15) == 0 && epi.ldm % 8 == 0 && epi.ob1 % 8 == 0 && epi.ob2 % 8 == 0;
     (void)a;
     if (epi.bias && !epi.bias_on_m) ok = ok && ((uintptr_t)epi.bias & 15) == 0;
     if (epi.resid)

@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   const int b = r / o.rows_per_stream;
   if (!s.active[r] || s.done[b]) return;
   __shared__ float red[16];
-  __shared__ float lkey[SR_THREADS][MAX_CAND];
-  __shared__ int ltok[SR_THREADS][MAX_CAND];
+  __shared__ float lkey[MAX_CAND][SR_THREADS];   // per-thread sorted lists, thread index fastest (no bank conflicts)
+  __shared__ int ltok[MAX_CAND][SR_THREADS];
   __shared__ float wkey[8];
   __shared__ int wtok[8], wtid[8];
   __shared__ int win_tid;
@@ -113,10 +113,22 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
 
   // pass 1: softmax statistics of the text part and the timestamp part after masks a-d
   float mt = -INFINITY, st = 0.f, mz = -INFINITY, sz = 0.f;
-  for (int t = tid; t < v.vocab; t += SR_THREADS) {
-    if (tok_masked(t, c)) continue;
-    if (t < v.ts_begin) lse_merge(mt, st, lg[t], 1.f);
-    else lse_merge(mz, sz, lg[t], 1.f);
+  const float4* lg4 = reinterpret_cast<const float4*>(lg);
+  const int n4 = v.vocab_ld >> 2;
+  auto stat = [&](int t, float x) {
+    if (t >= v.vocab || tok_masked(t, c)) return;
+    if (t < v.ts_begin) lse_merge(mt, st, x, 1.f);
+    else lse_merge(mz, sz, x, 1.f);
+  };
+  for (int i0 = tid; i0 < n4; i0 += 4 * SR_THREADS) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = (i0 + u * SR_THREADS < n4) ? lg4[i0 + u * SR_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = 4 * (i0 + u * SR_THREADS);
+      if (t < v.vocab) { stat(t, q[u].x); stat(t + 1, q[u].y); stat(t + 2, q[u].z); stat(t + 3, q[u].w); }
+    }
   }
   block_lse(mt, st, red);
   block_lse(mz, sz, red);
@@ -136,28 +148,38 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   int cnt = 0;
   uint32_t gkey = 0;
   if (o.sampling) gkey = hash_u32((o.seed * 0x9E3779B1u) ^ hash_u32((uint32_t)((b * 64 + (r - b * o.rows_per_stream)) * 65537 + s.step[b])));
-  for (int t = tid; t < v.vocab; t += SR_THREADS) {
-    if (tok_masked(t, c)) continue;
-    if (text_off && t < v.ts_begin) continue;
-    const float lp = lg[t] - lse;
+  auto consider = [&](int t, float x) {
+    if (t >= v.vocab || tok_masked(t, c)) return;
+    if (text_off && t < v.ts_begin) return;
+    const float lp = x - lse;
     float key = lp;
     if (o.sampling) {
       const double u = ((double)hash_u32((uint32_t)t ^ gkey) + 0.5) / 4294967296.0;
       key = __fdiv_rn(lp, o.temperature) + (float)(-log(-log(u)));
     }
-    if (cnt == NC && !(key > lkey[tid][NC - 1])) continue;
+    if (cnt == NC && !(key > lkey[NC - 1][tid])) return;
     int i = cnt < NC ? cnt : NC - 1;
-    while (i > 0 && key > lkey[tid][i - 1]) {
-      lkey[tid][i] = lkey[tid][i - 1]; ltok[tid][i] = ltok[tid][i - 1];
+    while (i > 0 && key > lkey[i - 1][tid]) {
+      lkey[i][tid] = lkey[i - 1][tid]; ltok[i][tid] = ltok[i - 1][tid];
       --i;
     }
-    lkey[tid][i] = key; ltok[tid][i] = t;
+    lkey[i][tid] = key; ltok[i][tid] = t;
     if (cnt < NC) ++cnt;
+  };
+  for (int i0 = tid; i0 < n4; i0 += 4 * SR_THREADS) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = (i0 + u * SR_THREADS < n4) ? lg4[i0 + u * SR_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = 4 * (i0 + u * SR_THREADS);
+      if (t < v.vocab) { consider(t, q[u].x); consider(t + 1, q[u].y); consider(t + 2, q[u].z); consider(t + 3, q[u].w); }
+    }
   }
   int hd = 0;
   for (int round = 0; round < NC; ++round) {
-    float k = hd < cnt ? lkey[tid][hd] : -INFINITY;
-    int t = hd < cnt ? ltok[tid][hd] : 0x7fffffff;
+    float k = hd < cnt ? lkey[hd][tid] : -INFINITY;
+    int t = hd < cnt ? ltok[hd][tid] : 0x7fffffff;
     int who = tid;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -176,8 +198,8 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
     }
     __syncthreads();
     if (tid == win_tid) {
-      s.cand_val[(long)r * MAX_CAND + round] = lg[ltok[tid][hd]] - lse;
-      s.cand_tok[(long)r * MAX_CAND + round] = ltok[tid][hd];
+      s.cand_val[(long)r * MAX_CAND + round] = lg[ltok[hd][tid]] - lse;
+      s.cand_tok[(long)r * MAX_CAND + round] = ltok[hd][tid];
       ++hd;
     }
     __syncthreads();

@@ -230,6 +230,7 @@ class _StreamJob:
                 self.all_tokens.extend(tokenizer.encode(" " + options.initial_prompt.strip()))
             else:
                 self.all_tokens.extend(options.initial_prompt)
+        self.single_window = False
         self.last_speech_timestamp = 0.0
         self.segments: List[Segment] = []
         self.n_emitted = 0
@@ -538,7 +539,9 @@ class B200WhisperModel:
             tok = Tokenizer(self.hf_tokenizer, self.model.is_multilingual, task=p["kw"]["task"], language=p["language"])
             opts = self._make_options(tok, p["kw"])
             p["options"] = opts
-            jobs.append((i, _StreamJob(self, p["features"], tok, opts), p))
+            job = _StreamJob(self, p["features"], tok, opts)
+            job.single_window = p["single_window"]
+            jobs.append((i, job, p))
         self._run_jobs([j for _, j, _ in jobs])
         for i, job, p in jobs:
             segs = job.segments
@@ -564,6 +567,7 @@ class B200WhisperModel:
                      language_detection_threshold=0.5, language_detection_segments=1)
 
     def _prepare_stream(self, audio: np.ndarray, kw: dict) -> Optional[dict]:
+        single_window = bool(kw.pop("_single_window", False))   # not part of the reference surface (bench.py only)
         full = dict(self._DEFAULTS)
         unknown = set(kw) - set(full)
         if unknown:
@@ -593,7 +597,7 @@ class B200WhisperModel:
             return None
         return dict(audio=np.ascontiguousarray(audio, dtype=np.float32), kw=kw, duration=duration,
                     duration_after_vad=duration_after_vad, speech_chunks=speech_chunks, vad_parameters=vad_parameters,
-                    language=None, language_probability=1, all_language_probs=None)
+                    language=None, language_probability=1, all_language_probs=None, single_window=single_window)
 
     def _resolve_languages(self, prepared: List[dict]) -> None:
         """Reference :868-907, batched: one detect_language pass over all streams that need it."""
@@ -681,6 +685,10 @@ class B200WhisperModel:
                 pending = sorted(nxt)
             for j, _ in live:
                 j.finish_window()
+                j.enc = None                      # give the encoder slots back before the next window
+                if j.single_window:
+                    j.seek = j.content_frames     # bench switch: one 30 s window per chunk (pinned work)
+            del enc
 
     def generate_segments(self, features: np.ndarray, tokenizer: Tokenizer, options: TranscriptionOptions,
                           log_progress=False, encoder_output=None) -> List[Segment]:
