@@ -24,7 +24,8 @@ from whisperlive_b200.weights import random_init
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 0.12       # fp16 logit tolerance (logit std is ~3)
-MARGIN_TOL = 0.20      # a token/beam decision closer than this may legitimately flip (two rows' logit errors add)
+MARGIN_TOL = 0.20      # a greedy token decision closer than this may legitimately flip
+SCORE_TOL = 0.05       # length-normalised hypothesis score: beam-search near-ties within this are interchangeable
 
 _ENGINES = {}
 
@@ -166,20 +167,53 @@ def test_teacher_forced_logits(name):
         assert err.max() < LOGIT_TOL
 
 
-def _compare_generation(got, ref, what):
-    """Equal, or diverging only where the oracle's own margin is within tolerance."""
+def _oracle_rescore(orc, oenc, b, prompt, seq, kw):
+    """Teacher-force the engine's hypothesis through the ORACLE (same logits processors) and return its
+    length-normalised score as the oracle would have scored it."""
+    from oracle.search import GenOptions, apply_processors, max_new_tokens
+    spec = orc.spec
+    opts = GenOptions(beam_size=kw.get("beam_size", 5), suppress_blank=kw.get("suppress_blank", True),
+                      suppress_tokens=[t for t in kw.get("suppress_tokens", ()) if t >= 0],
+                      max_initial_timestamp_index=kw.get("max_initial_timestamp_index", 50))
+    use_ts = prompt[-1] != spec.no_timestamps
+    step = orc._stream_step_fn(oenc, b)
+    if len(prompt) > 1:
+        step(torch.tensor([prompt[:-1]]), None)
+    n_new = max_new_tokens(len(prompt), kw.get("max_length", 448))
+    cum, gen, cur = 0.0, [], prompt[-1]
+    targets = list(seq) + ([spec.eot] if len(seq) < n_new else [])
+    for tok in targets:
+        logp = apply_processors(step(torch.tensor([[cur]]), None)[0, -1], gen, spec, opts, use_ts)
+        cum += float(logp[tok])
+        gen.append(tok)
+        cur = tok
+    lp = kw.get("length_penalty", 1)
+    return cum / (max(len(seq), 1) ** lp) if lp else cum
+
+
+def _compare_generation(got, ref, what, orc=None, oenc=None, prompts=None, kw=None):
+    """Token-exact, or a beam-search near-tie: a differing hypothesis is accepted only if (a) the engine's
+    own score for it agrees with the oracle's score of the SAME tokens (the numerics are right) and (b) that
+    score is within the fp16 tolerance of the oracle's best (so an fp16-sized logit perturbation can swap them)."""
     n_div = 0
     for b, (g, r) in enumerate(zip(got, ref)):
         gs, rs = g.sequences_ids[0], r.sequences_ids[0]
+        assert abs(g.no_speech_prob - r.no_speech_prob) < 0.02
         if gs == rs:
             assert abs(g.scores[0] - r.scores[0]) < 0.02, (what, b, g.scores, r.scores)
-            assert abs(g.no_speech_prob - r.no_speech_prob) < 0.02
             continue
         i = next((k for k, (x, y) in enumerate(zip(gs, rs)) if x != y), min(len(gs), len(rs)))
-        margins = r.margins[max(0, i - 1): i + 2]
-        print(f"{what} stream {b}: diverges at token {i} (oracle margins there {margins})")
-        assert margins and min(margins) < MARGIN_TOL, (what, b, i, gs[:i + 3], rs[:i + 3], margins)
         n_div += 1
+        if orc is None:
+            margins = r.margins[max(0, i - 1): i + 2]
+            print(f"{what} stream {b}: diverges at token {i} (oracle margins there {margins})")
+            assert margins and min(margins) < MARGIN_TOL, (what, b, i, margins)
+            continue
+        rescored = _oracle_rescore(orc, oenc, b, list(prompts[b]), gs, kw)
+        print(f"{what} stream {b}: diverges at token {i}/{len(rs)}: engine score {g.scores[0]:.4f}, oracle score of the "
+              f"engine's tokens {rescored:.4f}, oracle best {r.scores[0]:.4f}")
+        assert abs(rescored - g.scores[0]) < 0.03, (what, b, "engine score disagrees with the oracle on its own tokens")
+        assert rescored > r.scores[0] - SCORE_TOL, (what, b, "engine hypothesis is worse than the oracle's beyond tolerance")
     return n_div
 
 
@@ -196,8 +230,7 @@ def test_generate_matches_oracle(name, beam):
     kw = dict(beam_size=beam, suppress_tokens=sup, return_scores=True, return_no_speech_prob=True)
     got = eng.generate(enc, prompts, **kw)
     ref = orc.generate(oenc, prompts, **kw)
-    n_div = _compare_generation(got, ref, f"{name} beam{beam}")
-    assert n_div <= 2
+    n_div = _compare_generation(got, ref, f"{name} beam{beam}", orc, oenc, prompts, kw)
     lens = [len(g.sequences_ids[0]) for g in got]
     print(f"generate {name} beam {beam}: lengths {lens} steps {[g.steps for g in got]} divergences {n_div}")
 
@@ -230,7 +263,7 @@ def test_generate_options_and_errors():
     got = eng.generate(enc, [prompt], **kw)
     ref = orc.generate(oenc, [prompt], **kw)
     assert len(got[0].sequences_ids) == len(ref[0].sequences_ids) == 2
-    _compare_generation(got, ref, "options")
+    _compare_generation(got, ref, "options", orc, oenc, [prompt], kw)
     assert all(len(s) <= 20 for s in got[0].sequences_ids)
     with pytest.raises(RuntimeError):
         eng.generate(enc, [[sp.sot] * 448], beam_size=1)            # no room under max_length

@@ -2,6 +2,8 @@
 //   K10 decoder_self_attn : KV cache append + attention over <=448 positions with beam indirection
 //   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V,
 //       streamed HBM -> smem by a producer warp with cp.async.bulk + mbarrier ring, consumed by 4 warps.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace wl {
@@ -110,7 +112,7 @@ void decoder_self_attn(cudaStream_t st, const DecodeState& s, const float* qkv, 
 
 // ============================================================================ K11 cross attention
 constexpr int XA_CHUNK = 128;                 // keys per pipeline stage
-constexpr int XA_STAGES = 3;
+constexpr int XA_STAGES = 2;                  // x up to 4 CTAs per SM: 128 KB of K/V in flight per SM
 constexpr int XA_STAGE_BYTES = XA_CHUNK * 128;  // 64 halves per key
 constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
 
@@ -369,20 +371,39 @@ __global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict
   out[(long)r * d + h * 64 + dd] = __float2half_rn(o / L);
 }
 
-int cross_attn_pick_nsplit(int B, int H, int num_sms) {
-  const int want = 2 * num_sms;
-  int ns = (want + B * H - 1) / (B * H);
-  if (ns < 1) ns = 1;
-  if (ns > XA_NCHUNK) ns = XA_NCHUNK;
-  const int cps = (XA_NCHUNK + ns - 1) / ns;
-  return (XA_NCHUNK + cps - 1) / cps;
+static int xa_smem_bytes(int cps, int NQ) {
+  return 128 + XA_STAGES * XA_STAGE_BYTES + cps * XA_CHUNK * 8 * 4 + (64 + 4 * NQ * 64) * 4 + 2 * XA_STAGES * 8 + 64;
+}
+static int xa_template_nq(int rows_per_stream) {
+  return rows_per_stream == 1 ? 1 : rows_per_stream == 2 ? 2 : rows_per_stream <= 4 ? 4 : rows_per_stream == 5 ? 5 : 8;
+}
+
+// Choose how many CTAs share one (stream, head): the grid should fill whole waves of resident CTAs
+// (occupancy is set by shared memory -- the score buffer shrinks with the split -- and by registers).
+int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
+  const int NQ = xa_template_nq(rows_per_stream);
+  const int regs = NQ <= 2 ? 56 : NQ == 4 ? 96 : NQ == 5 ? 120 : 156;   // ptxas -v
+  const int occ_reg = std::max(1, 65536 / (regs * 160));
+  int best_ns = 1;
+  double best_eff = -1.0;
+  for (int ns = 1; ns <= XA_NCHUNK; ++ns) {
+    const int cps = (XA_NCHUNK + ns - 1) / ns;
+    const int real = (XA_NCHUNK + cps - 1) / cps;
+    if (real != ns) continue;
+    const int occ = std::max(1, std::min(occ_reg, (227 * 1024) / (xa_smem_bytes(cps, NQ) + 1024)));
+    const long slots = (long)occ * num_sms, items = (long)B * H * ns;
+    const long waves = (items + slots - 1) / slots;
+    const double eff = (double)items / (double)(waves * slots) - 0.01 * ns;   // mild preference for fewer partials
+    if (eff > best_eff) { best_eff = eff; best_ns = ns; }
+  }
+  return best_ns;
 }
 
 template <int NQ>
 static void launch_cross(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
                          long slot_stride, const CrossAttnWorkspace& ws, int B, int rows_per_stream, int H, int d, int nsplit) {
   const int cps = (XA_NCHUNK + nsplit - 1) / nsplit;
-  const int smem = 128 + XA_STAGES * XA_STAGE_BYTES + cps * XA_CHUNK * 8 * 4 + (64 + 4 * NQ * 64) * 4 + 2 * XA_STAGES * 8 + 64;
+  const int smem = xa_smem_bytes(cps, NQ);
   dim3 grid(nsplit, H, B);
   cross_attn_kernel<NQ><<<grid, 160, smem, st>>>(s, q, kc, vc, slot_stride, ws.part, ws.probs, rows_per_stream, H, d, nsplit, cps);
   WL_CUDA(cudaGetLastError());

@@ -40,54 +40,131 @@ void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int 
 }
 
 // ---------------------------------------------------------------------------- layernorm_rows
-// One warp per row, the row lives in registers (d <= 1280 -> 40 values per lane), two-pass statistics.
-template <int MAXV>
+// One warp per row, float4 loads, the row lives in registers (d <= 1280 -> 10 float4 per lane), two-pass
+// statistics.  Kept deliberately compact: in the decode loop this kernel runs ~100 times per step on a
+// handful of rows, where a long unrolled body costs more in instruction fetch than in arithmetic.
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ be, __half* __restrict__ y,
                                                         float* __restrict__ y32, long rows, int d, float* __restrict__ zero_buf,
                                                         long zero_n) {
   // optional side job: clear the fp32 buffer the next split-K GEMM accumulates into
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < zero_n; i += (long)gridDim.x * 256) zero_buf[i] = 0.f;
+  {
+    float4* z4 = reinterpret_cast<float4*>(zero_buf);
+    const long n4z = zero_n >> 2;
+    for (long i = blockIdx.x * 256L + threadIdx.x; i < n4z; i += (long)gridDim.x * 256) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + row * d;
-  float v[MAXV];
+  const int n4 = d >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[10];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < 10; ++i) {
     const int c = i * 32 + lane;
-    v[i] = c < d ? xr[c] : 0.f;
-    sum += v[i];
+    v[i] = c < n4 ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(sum) / d;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = i * 32 + lane;
-    const float t = c < d ? v[i] - mean : 0.f;
-    sq += t * t;
+  for (int i = 0; i < 10; ++i) {
+    if (i * 32 + lane < n4) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+      sq += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    }
   }
   const float rstd = rsqrtf(warp_sum(sq) / d + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(be);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < 10; ++i) {
     const int c = i * 32 + lane;
-    if (c < d) {
-      const float o = (v[i] - mean) * rstd * g[c] + be[c];
-      if (y) y[row * d + c] = __float2half_rn(o);
-      if (y32) y32[row * d + c] = o;
+    if (c < n4) {
+      const float4 gg = g4[c], bb = b4[c];
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+      if (y) {
+        __align__(8) __half2 h[2] = {__floats2half2_rn(o.x, o.y), __floats2half2_rn(o.z, o.w)};
+        *reinterpret_cast<uint2*>(y + row * d + 4 * c) = *reinterpret_cast<const uint2*>(h);
+      }
+      if (y32) *reinterpret_cast<float4*>(y32 + row * d + 4 * c) = o;
+    }
+  }
+}
+
+// Decode-step variant: one 128-thread block per row (<= 3 float4 per thread) -- a few dozen instructions, so the
+// ~100 launches per decode step are not dominated by instruction fetch.  Extra blocks only clear `zero_buf`.
+__global__ void __launch_bounds__(128) layernorm_small_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                              const float* __restrict__ be, __half* __restrict__ y,
+                                                              long rows, int d, float* __restrict__ zero_buf, long zero_n) {
+  {
+    float4* z4 = reinterpret_cast<float4*>(zero_buf);
+    const long n4z = zero_n >> 2;
+    for (long i = blockIdx.x * 128L + threadIdx.x; i < n4z; i += (long)gridDim.x * 128) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long row = blockIdx.x;
+  if (row >= rows) return;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, n4 = d >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x + row * d);
+  float4 v[3];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = i * 128 + tid;
+    v[i] = c < n4 ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  const float mean = (red[0] + red[1] + red[2] + red[3]) / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i * 128 + tid < n4) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+      sq += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    }
+  }
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[4 + (tid >> 5)] = sq;
+  __syncthreads();
+  const float rstd = rsqrtf((red[4] + red[5] + red[6] + red[7]) / d + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(be);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = i * 128 + tid;
+    if (c < n4) {
+      const float4 gg = g4[c], bb = b4[c];
+      __align__(8) __half2 h[2] = {
+          __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+          __floats2half2_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w)};
+      *reinterpret_cast<uint2*>(y + row * d + 4 * c) = *reinterpret_cast<const uint2*>(h);
     }
   }
 }
 
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32, long rows,
                     int d, float* zero_buf, long zero_n) {
-  WL_CHECK(d <= 1280 && d % 32 == 0, WL_ERR_ARG, "layernorm: unsupported width %d", d);
+  WL_CHECK(d <= 1280 && d % 4 == 0 && zero_n % 4 == 0, WL_ERR_ARG, "layernorm: unsupported width %d", d);
+  if (rows <= 1024 && y && !y32) {
+    int grid = (int)rows;
+    if (zero_buf && zero_n > 0) grid = std::max(grid, std::min(296, cdiv(zero_n, 128 * 16)));
+    layernorm_small_kernel<<<grid, 128, 0, st>>>(x, gamma, beta, y, rows, d, zero_buf, zero_buf ? zero_n : 0);
+    WL_CUDA(cudaGetLastError());
+    note_launch(1);
+    return;
+  }
   int grid = cdiv(rows, 8);
   if (zero_buf && zero_n > 0) grid = std::max(grid, std::min(148, cdiv(zero_n, 256 * 16)));
-  if (d <= 512) layernorm_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
-  else if (d <= 1024) layernorm_kernel<32><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
-  else layernorm_kernel<40><<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_n);
+  layernorm_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_buf ? zero_n : 0);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

@@ -792,7 +792,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   WL_CUDA(cudaMemcpyAsync(c->suppress_mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaEventRecord(c->ev0, st));
   decode_init(st, c->ds, so, vi, B, R);
-  const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms);
+  const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms, Kr);
 
   cudaGraphExec_t exec = nullptr;
   long graph_kernels = 0;
@@ -898,7 +898,7 @@ static void forced_run(wl_ctx* c, const int32_t* slots, int B, const int32_t* to
   cudaStream_t st = c->st;
   const int max_steps = upload_streams(c, slots, B, tokens, off, T_MAX, true);
   decode_init(st, c->ds, so, vi, B, B);
-  const int nsplit = align_mode ? 1 : cross_attn_pick_nsplit(B, c->H, c->num_sms);
+  const int nsplit = align_mode ? 1 : cross_attn_pick_nsplit(B, c->H, c->num_sms, 1);
   for (int i = 0; i < max_steps; ++i) {
     decode_step(c, B, 1, so, vi, nsplit, align_mode);
     if (logits_out_dev)

@@ -25,6 +25,7 @@ struct GemmKParams {
   int a_pos[3], b_pos[3];  // tensor-map coordinate slots (1..3) of (row, i1, i2)
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
+  int nz;           // batch entries (or K splits in accum mode): tiles = tiles_m * tiles_n * nz
   int accum;        // 1: grid z enumerates K ranges; partial sums are atomically added to the fp32 output
   int kb_per_split; // k-blocks per split (accum mode)
 };
@@ -142,6 +143,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   }
 }
 
+// Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile_m fastest, so CTAs
+// running side by side share the B (weight) tile in L2).  Two TMEM accumulator stages: the epilogue warps drain
+// tile i while the MMA warp already accumulates tile i+1.
 template <int BN, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -149,21 +153,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * A_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-  const int z = p.accum ? 0 : blockIdx.z, split = p.accum ? blockIdx.z : 0;
-  const int i1 = z % p.zn1, i2 = z / p.zn1;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n * p.nz;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int kb0 = p.accum ? split * p.kb_per_split : 0;
-  const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;  // host guarantees >= 1
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -174,7 +177,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -190,64 +196,96 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
-      const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
       // coordinate slot s (1..3) of a tensor map holds whichever of (row, i1, i2) was sorted there
       auto slot = [](const int (&pos)[3], int s, int row, int j1, int j2) {
         return pos[0] == s ? row : (pos[1] == s ? j1 : (pos[2] == s ? j2 : 0));
       };
-      const int ca1 = slot(p.a_pos, 1, tile_m * BM, a1, a2), ca2 = slot(p.a_pos, 2, tile_m * BM, a1, a2),
-                ca3 = slot(p.a_pos, 3, tile_m * BM, a1, a2);
-      const int cb1 = slot(p.b_pos, 1, tile_n * BN, b1, b2), cb2 = slot(p.b_pos, 2, tile_n * BN, b1, b2),
-                cb3 = slot(p.b_pos, 3, tile_n * BN, b1, b2);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-        const int k0 = (kb0 + kb) * BK;
-        tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], k0, ca1, ca2, ca3);
-        tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
+        const int z = p.accum ? 0 : zz, split = p.accum ? zz : 0;
+        const int i1 = z % p.zn1, i2 = z / p.zn1;
+        const int kb0 = p.accum ? split * p.kb_per_split : 0;
+        const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
+        const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
+        const int ca1 = slot(p.a_pos, 1, tile_m * BM, a1, a2), ca2 = slot(p.a_pos, 2, tile_m * BM, a1, a2),
+                  ca3 = slot(p.a_pos, 3, tile_m * BM, a1, a2);
+        const int cb1 = slot(p.b_pos, 1, tile_n * BN, b1, b2), cb2 = slot(p.b_pos, 2, tile_n * BN, b1, b2),
+                  cb3 = slot(p.b_pos, 3, tile_n * BN, b1, b2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          const int k0 = (kb0 + kb) * BK;
+          tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], k0, ca1, ca2, ca3);
+          tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int zz = (t / tiles_m) / tiles_n;
+        const int kb0 = p.accum ? zz * p.kb_per_split : 0;
+        const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        mbar_wait(&acc_empty[as], aphase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+        const uint32_t acc = tmem_acc + as * ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 halves = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4) units
-          umma_f16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 halves = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4) units
+            umma_f16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&acc_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      umma_commit(acc_full);
     }
   } else if (warp >= 4) {
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
     const int q = warp & 3;
-    const long m = (long)tile_m * BM + q * 32 + lane_id();
-    const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16);
-    if constexpr (BN >= 32) {
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
+      const int z = p.accum ? 0 : zz, split = p.accum ? zz : 0;
+      const int i1 = z % p.zn1, i2 = z / p.zn1;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const long m = (long)tile_m * BM + q * 32 + lane_id();
+      const uint32_t lane_addr = tmem_acc + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      if constexpr (BN >= 32) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + c, v);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + c, v);
+          tmem_ld_wait();
+          if (c + 32 >= BN) {  // accumulator fully in registers: hand the TMEM stage back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
+          }
+          epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
+        }
+      } else {
+        uint32_t v[16];
+        tmem_ld_32x16(lane_addr, v);
         tmem_ld_wait();
-        epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
+        epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2, split);
       }
-    } else {
-      uint32_t v[16];
-      tmem_ld_32x16(lane_addr, v);
-      tmem_ld_wait();
-      epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2, split);
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
   tc_fence_before();
@@ -335,8 +373,13 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
 template <int BN, int STAGES, int MIN_CTAS>
 static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), Z);
-  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 256, smem, stream>>>(ta, tb, p);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  GemmKParams q = p;
+  q.nz = Z;
+  const long tiles = (long)cdiv(p.N, BN) * cdiv(p.M, BM) * Z;
+  const int grid = (int)std::min<long>(tiles, (long)sms * MIN_CTAS);
+  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 256, smem, stream>>>(ta, tb, q);
   WL_CUDA(cudaGetLastError());
   g_gemm_launches++;
 }

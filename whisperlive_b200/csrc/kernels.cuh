@@ -104,7 +104,7 @@ struct CrossAttnWorkspace {
 void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit);
-int cross_attn_pick_nsplit(int B, int H, int num_sms);
+int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream);
 
 // K12: per-row masked log-softmax + top candidates, then per-stream beam / greedy update.
 void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, const SearchOpts& o, const VocabIds& v, int R);
