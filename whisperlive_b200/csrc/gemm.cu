@@ -25,6 +25,7 @@ struct GemmKParams {
   int a_pos[3], b_pos[3];  // tensor-map coordinate slots (1..3) of (row, i1, i2)
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
+  int row_store;    // row-major / head-split output: coalesced stores through the smem transpose
   int nz;           // batch entries (or K splits in accum mode): tiles = tiles_m * tiles_n * nz
   int accum;        // 1: grid z enumerates K ranges; partial sums are atomically added to the fp32 output
   int kb_per_split; // k-blocks per split (accum mode)
@@ -143,6 +144,43 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   }
 }
 
+// Coalesced epilogue for row-major outputs: the warp's 32x32 accumulator chunk (lane = row) is transposed through
+// a padded smem tile so that every global access of the warp covers one contiguous row segment (lane = column).
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, long m0, int n0, const float* stg, int lane, int i1, int i2) {
+  const GemmEpilogue& e = p.e;
+  const int n = n0 + lane;
+  const bool ncol = n < p.N;
+  const float bias_n = (e.bias && !e.bias_on_m && ncol) ? e.bias[n] : 0.f;
+  if (e.mode == GEMM_HEADSPLIT) {
+    const int h = n >> 6, dd = n & 63;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const long m = m0 + r;
+      if (m >= p.M) break;
+      const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
+      if (ncol)
+        ((__half*)e.out)[(long)e.hs_slots[b] * e.hs_slot_stride + ((long)h * e.hs_S + s) * 64 + dd] =
+            __float2half_rn(stg[r * 33 + lane] + bias_n);
+    }
+    return;
+  }
+  const long ob = (long)i1 * e.ob1 + (long)i2 * e.ob2 + n;
+  const long rb = (long)i1 * e.rb1 + (long)i2 * e.rb2 + n;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const long m = m0 + r;
+    if (m >= p.M) break;
+    float x = stg[r * 33 + lane] + bias_n;
+    if (e.bias && e.bias_on_m) x += e.bias[m];
+    if (e.gelu) x = gelu_erf(x);
+    if (ncol) {
+      if (e.resid) x += e.resid[rb + m * e.rldm];
+      if (e.out_f32) ((float*)e.out)[ob + m * e.ldm] = x;
+      else ((__half*)e.out)[ob + m * e.ldm] = __float2half_rn(x);
+    }
+  }
+}
+
 // Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile_m fastest, so CTAs
 // running side by side share the B (weight) tile in L2).  Two TMEM accumulator stages: the epilogue warps drain
 // tile i while the MMA warp already accumulates tile i+1.
@@ -162,6 +200,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* stage_out = reinterpret_cast<float*>(tmem_slot + 4);   // 4 warps x [32][33] floats (row-store epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -274,7 +313,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
           }
-          epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
+          if (p.row_store) {
+            float* stg = stage_out + q * (32 * 33);
+            const int ln = lane_id();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) stg[ln * 33 + i] = __uint_as_float(v[i]);
+            __syncwarp();
+            epilogue_rows(p, (long)tile_m * BM + q * 32, tile_n * BN + c, stg, ln, i1, i2);
+            __syncwarp();
+          } else {
+            epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
+          }
         }
       } else {
         uint32_t v[16];
@@ -372,7 +421,7 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
 
 template <int BN, int STAGES, int MIN_CTAS>
 static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + 4 * 32 * 33 * 4;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   GemmKParams q = p;
@@ -386,7 +435,7 @@ static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
 
 template <int BN, int STAGES, int MIN_CTAS>
 static void prime_cfg() {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + 4 * 32 * 33 * 4;
   WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
@@ -394,11 +443,9 @@ static void prime_cfg() {
 void gemm_prime() {
   prime_cfg<16, 8, 1>();
   prime_cfg<32, 8, 1>();
-  prime_cfg<64, 4, 2>();
-  prime_cfg<128, 3, 2>();
   prime_cfg<256, 4, 1>();
   prime_cfg<64, 8, 1>();
-  prime_cfg<128, 6, 1>();
+  prime_cfg<128, 5, 1>();
 }
 
 static int env_int(const char* name, int dflt) {
@@ -448,17 +495,31 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   else if (N <= 16) bn = 16;
   else if (N <= 32) bn = 32;
   else if (N <= 64) bn = 64;
-  else if (N % 256 == 0 && M >= 1024 && epi.ldn == 1 && epi.mode == GEMM_STORE) bn = 256;
+  else if (N >= 512 && M >= 512 && epi.ldn == 1) bn = 256;
   else bn = 128;
   if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
-  const bool skinny = epi.ldm == 1 && epi.mode == GEMM_STORE;  // swap-AB decode GEMM: few tiles, deep pipeline
+  p.row_store = (!epi.accumulate && epi.ldn == 1 && bn >= 32) ? 1 : 0;
   if (epi.accumulate) {
     WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && epi.mode == GEMM_STORE, WL_ERR_ARG,
              "gemm_tn: accumulate (split-K) needs a plain fp32 output");
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int tiles = cdiv(N, bn) * cdiv(M, BM), total_kb = cdiv(K, BK);
-    int splits = tiles >= sms ? 1 : std::min(total_kb, std::max(1, sms / tiles));
+    // Cost model (measured on B200): a CTA streams its share of the weights at ~100 GB/s (latency-bound TMA ring),
+    // and the fp32 atomics of the epilogue retire at ~1.3 cycles per element per SM.  More splits shorten the
+    // stream but multiply the atomics (M*N per split): pick the split count that minimises the larger of the two.
+    int splits = 1;
+    {
+      const int max_s = tiles >= sms ? 1 : std::min(total_kb, std::max(1, sms / tiles));
+      double best = 1e30;
+      for (int s = 1; s <= max_s; ++s) {
+        const int kbs = cdiv(total_kb, s);
+        const double t_stream = (double)kbs * BK * 2.0 * (BM + bn) / 100e9;
+        const double t_atomic = (double)M * N * cdiv(total_kb, kbs) * 1.3 / (sms * 1.9e9);
+        const double cost = std::max(t_stream, t_atomic) + 0.05e-6 * s;
+        if (cost < best) { best = cost; splits = s; }
+      }
+    }
     p.accum = 1;
     p.kb_per_split = cdiv(total_kb, splits);
     Z = cdiv(total_kb, p.kb_per_split);
@@ -470,14 +531,8 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   switch (bn) {
     case 16: launch_cfg<16, 8, 1>(stream, ta, tb, p, Z); break;
     case 32: launch_cfg<32, 8, 1>(stream, ta, tb, p, Z); break;
-    case 64:
-      if (skinny) launch_cfg<64, 8, 1>(stream, ta, tb, p, Z);
-      else launch_cfg<64, 4, 2>(stream, ta, tb, p, Z);
-      break;
-    case 128:
-      if (skinny) launch_cfg<128, 6, 1>(stream, ta, tb, p, Z);
-      else launch_cfg<128, 3, 2>(stream, ta, tb, p, Z);
-      break;
+    case 64: launch_cfg<64, 8, 1>(stream, ta, tb, p, Z); break;
+    case 128: launch_cfg<128, 5, 1>(stream, ta, tb, p, Z); break;
     case 256: launch_cfg<256, 4, 1>(stream, ta, tb, p, Z); break;
     default: WL_CHECK(false, WL_ERR_ARG, "unsupported BN %d", bn);
   }
