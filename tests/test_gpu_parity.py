@@ -213,7 +213,12 @@ def _compare_generation(got, ref, what, orc=None, oenc=None, prompts=None, kw=No
         print(f"{what} stream {b}: diverges at token {i}/{len(rs)}: engine score {g.scores[0]:.4f}, oracle score of the "
               f"engine's tokens {rescored:.4f}, oracle best {r.scores[0]:.4f}")
         assert abs(rescored - g.scores[0]) < 0.03, (what, b, "engine score disagrees with the oracle on its own tokens")
-        assert rescored > r.scores[0] - SCORE_TOL, (what, b, "engine hypothesis is worse than the oracle's beyond tolerance")
+        if kw.get("beam_size", 5) == 1:
+            # greedy: a divergence is a local decision; the oracle's own margin there must be tiny
+            margins = r.margins[max(0, i - 1): i + 2]
+            assert margins and min(margins) < MARGIN_TOL, (what, b, i, margins)
+        # beam search: one pruning near-tie can change the final hypothesis (and its score) arbitrarily, so the
+        # score gap is informational; the search LOGIC is pinned exactly by test_search_logic_exact_on_engine_logits
     return n_div
 
 
@@ -233,6 +238,59 @@ def test_generate_matches_oracle(name, beam):
     n_div = _compare_generation(got, ref, f"{name} beam{beam}", orc, oenc, prompts, kw)
     lens = [len(g.sequences_ids[0]) for g in got]
     print(f"generate {name} beam {beam}: lengths {lens} steps {[g.steps for g in got]} divergences {n_div}")
+
+
+class _EngineStep:
+    """oracle.search step function backed by the ENGINE's logits (teacher-forced wl_decode_logits over the
+    full prefix of every live row): lets the oracle's search run on exactly the numbers the engine sees."""
+
+    def __init__(self, eng, enc_b, prompt):
+        self.eng, self.enc_b = eng, enc_b
+        self.rows = [[]]
+        self.prompt = list(prompt)
+
+    def __call__(self, tokens, parents):
+        if parents is not None:
+            self.rows = [list(self.rows[int(p)]) for p in parents]
+        t_new = tokens.shape[1]
+        if tokens.shape[0] != len(self.rows):
+            self.rows = [list(self.rows[0]) for _ in range(tokens.shape[0])]
+        for r, row in enumerate(self.rows):
+            row.extend(int(t) for t in tokens[r])
+        enc = self.enc_b.select([0] * len(self.rows))
+        out = self.eng.decode_logits(enc, self.rows)
+        return torch.from_numpy(np.stack([o[-t_new:] for o in out]))
+
+
+@pytest.mark.parametrize("beam", [1, 5])
+def test_search_logic_exact_on_engine_logits(beam):
+    """Search-logic parity isolated from numerics: the oracle's search driven by the engine's own logits must
+    reproduce the engine's device-side search token for token (beam bookkeeping, timestamp rules, suppression,
+    hypothesis finalisation, length normalisation)."""
+    from oracle.search import GenOptions, search_stream
+    eng, orc = engine("micro.en", seed=0, max_streams=8)
+    dims = eng.dims
+    sp = orc.spec
+    feats = np.stack([feats_for(dims, 6.0, 1), feats_for(dims, 6.0, 2), feats_for(dims, 14.0, 7)])
+    enc = eng.encode(feats)
+    prompts = [[sp.sot], [sp.timestamp_begin - 3, 400, 1234, 11, sp.sot], [sp.sot]]
+    sup = [1, 2, 3, 50]
+    got = eng.generate(enc, prompts, beam_size=beam, num_hypotheses=min(beam, 3), suppress_tokens=sup, max_length=120)
+    n_exact = 0
+    for b, prompt in enumerate(prompts):
+        opts = GenOptions(beam_size=beam, num_hypotheses=min(beam, 3), suppress_tokens=sup, max_length=120)
+        ref = search_stream(_EngineStep(eng, enc.select([b]), prompt), list(prompt), sp, opts, stream_index=b)
+        same = ref.sequences_ids == got[b].sequences_ids
+        n_exact += same
+        print(f"beam {beam} stream {b}: exact={same} steps {got[b].steps} vs {ref.steps + len(prompt) - 1} "
+              f"min margin {min(ref.margins):.2e}")
+        if same:
+            np.testing.assert_allclose(got[b].scores, ref.scores, atol=2e-3)
+            assert abs(got[b].no_speech_prob - ref.no_speech_prob) < 1e-3
+        else:
+            # only an exact-tie-sized margin (split-K summation order) may explain a difference
+            assert min(ref.margins) < 2e-3, (b, got[b].sequences_ids[0][:8], ref.sequences_ids[0][:8])
+    assert n_exact >= 2
 
 
 def test_generate_sampling_matches_oracle():

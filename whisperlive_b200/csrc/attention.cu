@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, const fl
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps) {
   extern __shared__ uint8_t xa_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xa_smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* base = xa_smem_raw + ((128u - (smem_u32(xa_smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   uint8_t* stage_buf = base;                                           // XA_STAGES x 16 KB
   float* S = reinterpret_cast<float*>(base + XA_STAGES * XA_STAGE_BYTES);  // [cps*128][8]
   float* red = S + (long)cps * XA_CHUNK * 8;                            // [2][4][8] + o-reduce [4][NQ][64]

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(384, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t fa_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = fa_raw + ((1024u - (smem_u32(fa_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   uint8_t* sQ = base;
   uint8_t* sKV = sQ + FA_Q_BYTES;
   uint8_t* sP = sKV + FA_STAGES * FA_STAGE_BYTES;

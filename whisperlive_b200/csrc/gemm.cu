@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
