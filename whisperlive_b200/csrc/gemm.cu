@@ -1,8 +1,8 @@
 // tcgen05 GEMM: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (single issuing thread) -> TMEM
 // accumulator -> tcgen05.ld epilogue (bias / GELU / residual / layout transforms fused).
 //
-// CTA = 256 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps4-7 epilogue
-// (thread i of the epilogue group owns accumulator row i = TMEM lane i).  Tile 128 x BN x 64.
+// CTA = 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps4-11 epilogue
+// (lane i of TMEM = accumulator row i; two warps per 32-row group split the columns).  Tile 128 x BN x 64.
 #include "gemm.cuh"
 
 #include <algorithm>
@@ -25,7 +25,6 @@ struct GemmKParams {
   int a_pos[3], b_pos[3];  // tensor-map coordinate slots (1..3) of (row, i1, i2)
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
-  int row_store;    // row-major / head-split output: coalesced stores through the smem transpose
   int nz;           // batch entries (or K splits in accum mode): tiles = tiles_m * tiles_n * nz
   int accum;        // 1: grid z enumerates K ranges; partial sums are atomically added to the fp32 output
   int kb_per_split; // k-blocks per split (accum mode)
@@ -144,48 +143,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   }
 }
 
-// Coalesced epilogue for row-major outputs: the warp's 32x32 accumulator chunk (lane = row) is transposed through
-// a padded smem tile so that every global access of the warp covers one contiguous row segment (lane = column).
-__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, long m0, int n0, const float* stg, int lane, int i1, int i2) {
-  const GemmEpilogue& e = p.e;
-  const int n = n0 + lane;
-  const bool ncol = n < p.N;
-  const float bias_n = (e.bias && !e.bias_on_m && ncol) ? e.bias[n] : 0.f;
-  if (e.mode == GEMM_HEADSPLIT) {
-    const int h = n >> 6, dd = n & 63;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const long m = m0 + r;
-      if (m >= p.M) break;
-      const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
-      if (ncol)
-        ((__half*)e.out)[(long)e.hs_slots[b] * e.hs_slot_stride + ((long)h * e.hs_S + s) * 64 + dd] =
-            __float2half_rn(stg[r * 33 + lane] + bias_n);
-    }
-    return;
-  }
-  const long ob = (long)i1 * e.ob1 + (long)i2 * e.ob2 + n;
-  const long rb = (long)i1 * e.rb1 + (long)i2 * e.rb2 + n;
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const long m = m0 + r;
-    if (m >= p.M) break;
-    float x = stg[r * 33 + lane] + bias_n;
-    if (e.bias && e.bias_on_m) x += e.bias[m];
-    if (e.gelu) x = gelu_erf(x);
-    if (ncol) {
-      if (e.resid) x += e.resid[rb + m * e.rldm];
-      if (e.out_f32) ((float*)e.out)[ob + m * e.ldm] = x;
-      else ((__half*)e.out)[ob + m * e.ldm] = __float2half_rn(x);
-    }
-  }
-}
-
 // Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile_m fastest, so CTAs
 // running side by side share the B (weight) tile in L2).  Two TMEM accumulator stages: the epilogue warps drain
 // tile i while the MMA warp already accumulates tile i+1.
 template <int BN, int STAGES, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS)
+__global__ void __launch_bounds__(384, MIN_CTAS)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -200,7 +162,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* stage_out = reinterpret_cast<float*>(tmem_slot + 4);   // 4 warps x [32][33] floats (row-store epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -218,7 +179,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], BN >= 64 ? 8 : 4);
     }
     mbar_fence_init();
   }
@@ -290,8 +251,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (BN >= 64 || warp < 8)) {
+    // 8 epilogue warps (2 per SM sub-partition): warps 4-7 drain the left half of the accumulator columns,
+    // warps 8-11 the right half; narrow tiles (BN < 64) use warps 4-7 only.
     const int q = warp & 3;
+    constexpr int NH = BN >= 64 ? 2 : 1, HC = BN / NH;   // column halves, columns per half
+    const int c_lo = ((warp - 4) >> 2) * HC;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -304,26 +269,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t lane_addr = tmem_acc + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
       if constexpr (BN >= 32) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c_lo; c < c_lo + HC; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + c, v);
           tmem_ld_wait();
-          if (c + 32 >= BN) {  // accumulator fully in registers: hand the TMEM stage back before the stores
+          if (c + 32 >= c_lo + HC) {  // this warp's columns are in registers: hand the TMEM stage back before the stores
             tc_fence_before();
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
           }
-          if (p.row_store) {
-            float* stg = stage_out + q * (32 * 33);
-            const int ln = lane_id();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) stg[ln * 33 + i] = __uint_as_float(v[i]);
-            __syncwarp();
-            epilogue_rows(p, (long)tile_m * BM + q * 32, tile_n * BN + c, stg, ln, i1, i2);
-            __syncwarp();
-          } else {
-            epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
-          }
+          epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
         }
       } else {
         uint32_t v[16];
@@ -421,21 +376,21 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
 
 template <int BN, int STAGES, int MIN_CTAS>
 static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + 4 * 32 * 33 * 4;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   GemmKParams q = p;
   q.nz = Z;
   const long tiles = (long)cdiv(p.N, BN) * cdiv(p.M, BM) * Z;
   const int grid = (int)std::min<long>(tiles, (long)sms * MIN_CTAS);
-  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 256, smem, stream>>>(ta, tb, q);
+  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 384, smem, stream>>>(ta, tb, q);
   WL_CUDA(cudaGetLastError());
   g_gemm_launches++;
 }
 
 template <int BN, int STAGES, int MIN_CTAS>
 static void prime_cfg() {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + 4 * 32 * 33 * 4;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
@@ -498,7 +453,6 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   else if (N >= 512 && M >= 512 && epi.ldn == 1) bn = 256;
   else bn = 128;
   if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
-  p.row_store = (!epi.accumulate && epi.ldn == 1 && bn >= 32) ? 1 : 0;
   if (epi.accumulate) {
     WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && epi.mode == GEMM_STORE, WL_ERR_ARG,
              "gemm_tn: accumulate (split-K) needs a plain fp32 output");
