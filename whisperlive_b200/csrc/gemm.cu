@@ -34,12 +34,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 halves = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
-template <int cnt>
+// Epilogue kinds are compile-time so that every kernel instantiation carries exactly one, compact epilogue: the
+// decode-step GEMMs run ~200 times per step on a few CTAs each, where instruction fetch of a fat multi-path
+// epilogue costs more than its arithmetic.
+enum EpiKind : int { EPI_ROW = 0, EPI_COL = 1, EPI_ACCUM = 2, EPI_HEADSPLIT = 3 };
+
+template <int cnt, int KIND>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2,
                                                int split = 0) {
   const GemmEpilogue& e = p.e;
   if (m >= p.M) return;
-  if (p.accum) {
+  if constexpr (KIND == EPI_ACCUM) {
     // split-K: out (fp32, already holding the residual or zeros) += partial (+ bias from split 0)
     const long ob = m * e.ldm;
     const float bm0 = (split == 0 && e.bias && e.bias_on_m) ? e.bias[m] : 0.f;
@@ -54,7 +59,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
     }
     return;
   }
-  if constexpr (cnt >= 8) if (e.mode == GEMM_HEADSPLIT) {
+  if constexpr (KIND == EPI_HEADSPLIT && cnt >= 8) {
     // m = (b, s), n = (h, dd); one thread writes cnt (<=32) consecutive dd of one head row
     const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
     const int h = n0 >> 6, dd = n0 & 63;
@@ -79,7 +84,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   const long obase = (long)i1 * e.ob1 + (long)i2 * e.ob2 + m * e.ldm;
   const long rbase = (long)i1 * e.rb1 + (long)i2 * e.rb2 + m * e.rldm;
   const float bm = (e.bias && e.bias_on_m) ? e.bias[m] : 0.f;
-  if constexpr (cnt >= 8) if (p.vec_ok) {
+  if constexpr (KIND == EPI_ROW && cnt >= 8) {
 #pragma unroll
     for (int i = 0; i < cnt; i += 8) {
       const int n = n0 + i;
@@ -129,6 +134,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
     }
     return;
   }
+  if constexpr (KIND == EPI_COL || cnt < 8) {
 #pragma unroll
   for (int i = 0; i < cnt; ++i) {
     const int n = n0 + i;
@@ -141,12 +147,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
     if (e.out_f32) ((float*)e.out)[o] = x;
     else ((__half*)e.out)[o] = __float2half_rn(x);
   }
+  }
 }
 
 // Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile_m fastest, so CTAs
 // running side by side share the B (weight) tile in L2).  Two TMEM accumulator stages: the epilogue warps drain
 // tile i while the MMA warp already accumulates tile i+1.
-template <int BN, int STAGES, int MIN_CTAS>
+template <int BN, int STAGES, int MIN_CTAS, int KIND>
 __global__ void __launch_bounds__(384, MIN_CTAS)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmKParams p) {
@@ -202,10 +209,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
-        const int z = p.accum ? 0 : zz, split = p.accum ? zz : 0;
+        const int z = KIND == EPI_ACCUM ? 0 : zz, split = KIND == EPI_ACCUM ? zz : 0;
         const int i1 = z % p.zn1, i2 = z / p.zn1;
-        const int kb0 = p.accum ? split * p.kb_per_split : 0;
-        const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        const int kb0 = KIND == EPI_ACCUM ? split * p.kb_per_split : 0;
+        const int num_kb = KIND == EPI_ACCUM ? min(p.kb_per_split, total_kb - kb0) : total_kb;
         const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
         const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
         const int ca1 = slot(p.a_pos, 1, tile_m * BM, a1, a2), ca2 = slot(p.a_pos, 2, tile_m * BM, a1, a2),
@@ -229,8 +236,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int zz = (t / tiles_m) / tiles_n;
-        const int kb0 = p.accum ? zz * p.kb_per_split : 0;
-        const int num_kb = p.accum ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        const int kb0 = KIND == EPI_ACCUM ? zz * p.kb_per_split : 0;
+        const int num_kb = KIND == EPI_ACCUM ? min(p.kb_per_split, total_kb - kb0) : total_kb;
         mbar_wait(&acc_empty[as], aphase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t acc = tmem_acc + as * ACC_COLS;
@@ -261,7 +268,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
-      const int z = p.accum ? 0 : zz, split = p.accum ? zz : 0;
+      const int z = KIND == EPI_ACCUM ? 0 : zz, split = KIND == EPI_ACCUM ? zz : 0;
       const int i1 = z % p.zn1, i2 = z / p.zn1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -278,7 +285,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
           }
-          epilogue_chunk<32>(p, m, tile_n * BN + c, v, i1, i2, split);
+          epilogue_chunk<32, KIND>(p, m, tile_n * BN + c, v, i1, i2, split);
         }
       } else {
         uint32_t v[16];
@@ -287,7 +294,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
-        epilogue_chunk<16>(p, m, tile_n * BN, v, i1, i2, split);
+        epilogue_chunk<16, KIND>(p, m, tile_n * BN, v, i1, i2, split);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -374,7 +381,7 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
   return info;
 }
 
-template <int BN, int STAGES, int MIN_CTAS>
+template <int BN, int STAGES, int MIN_CTAS, int KIND>
 static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   static int sms = 0;
@@ -383,24 +390,43 @@ static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
   q.nz = Z;
   const long tiles = (long)cdiv(p.N, BN) * cdiv(p.M, BM) * Z;
   const int grid = (int)std::min<long>(tiles, (long)sms * MIN_CTAS);
-  gemm_tn_kernel<BN, STAGES, MIN_CTAS><<<grid, 384, smem, stream>>>(ta, tb, q);
+  gemm_tn_kernel<BN, STAGES, MIN_CTAS, KIND><<<grid, 384, smem, stream>>>(ta, tb, q);
   WL_CUDA(cudaGetLastError());
   g_gemm_launches++;
 }
 
-template <int BN, int STAGES, int MIN_CTAS>
+template <int BN, int STAGES, int MIN_CTAS, int KIND>
 static void prime_cfg() {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
-  WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
 // opt-in shared memory sizes must be set outside stream capture: done once from wl_init
+template <int KIND>
+static void prime_kind() {
+  prime_cfg<16, 8, 1, KIND>();
+  prime_cfg<32, 8, 1, KIND>();
+  prime_cfg<64, 8, 1, KIND>();
+  prime_cfg<128, 5, 1, KIND>();
+  prime_cfg<256, 4, 1, KIND>();
+}
 void gemm_prime() {
-  prime_cfg<16, 8, 1>();
-  prime_cfg<32, 8, 1>();
-  prime_cfg<256, 4, 1>();
-  prime_cfg<64, 8, 1>();
-  prime_cfg<128, 5, 1>();
+  prime_kind<EPI_ROW>();
+  prime_kind<EPI_COL>();
+  prime_kind<EPI_ACCUM>();
+  prime_kind<EPI_HEADSPLIT>();
+}
+
+template <int KIND>
+static void launch_kind(int bn, cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
+  switch (bn) {
+    case 16: launch_cfg<16, 8, 1, KIND>(stream, ta, tb, p, Z); break;
+    case 32: launch_cfg<32, 8, 1, KIND>(stream, ta, tb, p, Z); break;
+    case 64: launch_cfg<64, 8, 1, KIND>(stream, ta, tb, p, Z); break;
+    case 128: launch_cfg<128, 5, 1, KIND>(stream, ta, tb, p, Z); break;
+    case 256: launch_cfg<256, 4, 1, KIND>(stream, ta, tb, p, Z); break;
+    default: WL_CHECK(false, WL_ERR_ARG, "unsupported BN %d", bn);
+  }
 }
 
 static int env_int(const char* name, int dflt) {
@@ -482,14 +508,10 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   const CUtensorMap& ta = ia.tm;
   const CUtensorMap& tb = ib.tm;
   for (int i = 0; i < 3; ++i) { p.a_pos[i] = ia.pos[i]; p.b_pos[i] = ib.pos[i]; }
-  switch (bn) {
-    case 16: launch_cfg<16, 8, 1>(stream, ta, tb, p, Z); break;
-    case 32: launch_cfg<32, 8, 1>(stream, ta, tb, p, Z); break;
-    case 64: launch_cfg<64, 8, 1>(stream, ta, tb, p, Z); break;
-    case 128: launch_cfg<128, 5, 1>(stream, ta, tb, p, Z); break;
-    case 256: launch_cfg<256, 4, 1>(stream, ta, tb, p, Z); break;
-    default: WL_CHECK(false, WL_ERR_ARG, "unsupported BN %d", bn);
-  }
+  if (p.accum) launch_kind<EPI_ACCUM>(bn, stream, ta, tb, p, Z);
+  else if (epi.mode == GEMM_HEADSPLIT) launch_kind<EPI_HEADSPLIT>(bn, stream, ta, tb, p, Z);
+  else if (p.vec_ok) launch_kind<EPI_ROW>(bn, stream, ta, tb, p, Z);
+  else launch_kind<EPI_COL>(bn, stream, ta, tb, p, Z);
 }
 
 // ------------------------------------------------------------------------------------ SIMT reference
@@ -521,7 +543,7 @@ __global__ void gemm_tn_simt_kernel(GemmOperand A, GemmOperand B, GemmKParams p)
     ((__half*)e.out)[(long)e.hs_slots[bb] * e.hs_slot_stride + ((long)(n >> 6) * e.hs_S + s) * 64 + (n & 63)] = __float2half_rn(x);
     return;
   }
-  epilogue_chunk<1>(q, m, (int)n, v, i1, i2);
+  epilogue_chunk<1, EPI_COL>(q, m, (int)n, v, i1, i2);
 }
 
 void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& epi) {
