@@ -9,7 +9,7 @@
 namespace wl {
 
 // ============================================================================ K10 self attention
-__global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, const float* __restrict__ qkv, __half* __restrict__ kc,
+__global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSrc qkv, __half* __restrict__ kc,
                                                         __half* __restrict__ vc, long row_stride, __half* __restrict__ out,
                                                         int H, int d) {
   const int r = blockIdx.y, h = blockIdx.x, tid = threadIdx.x;
@@ -22,9 +22,15 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, const flo
   __shared__ float opart[16][64];
 
   if (tid < 64) {
-    const float* row = qkv + (long)r * 3 * d + h * 64 + tid;
-    q[tid] = row[0] * 0.125f;
-    const float kv = row[d], vv = row[2 * d];
+    // q / k / v of this (row, head): bias + the split-K partial sums, in order
+    const long off = (long)r * 3 * d + h * 64 + tid;
+    float qv = 0.f, kv = 0.f, vv = 0.f;
+    if (qkv.bias) { qv = qkv.bias[h * 64 + tid]; kv = qkv.bias[d + h * 64 + tid]; vv = qkv.bias[2 * d + h * 64 + tid]; }
+    for (int sp = 0; sp < qkv.nsplit; ++sp) {
+      const float* row = qkv.ptr + (long)sp * qkv.stride + off;
+      qv += row[0]; kv += row[d]; vv += row[2 * d];
+    }
+    q[tid] = qv * 0.125f;
     knew[tid] = kv;
     vnew[tid] = vv;
     const long o = (long)r * row_stride + ((long)h * T_MAX + pos) * 64 + tid;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, const flo
   }
 }
 
-void decoder_self_attn(cudaStream_t st, const DecodeState& s, const float* qkv, __half* kcache, __half* vcache,
+void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
                        long cache_row_stride, __half* out, int R, int H, int d) {
   dim3 grid(H, R);
   self_attn_kernel<<<grid, 128, 0, st>>>(s, qkv, kcache, vcache, cache_row_stride, out, H, d);
@@ -119,7 +125,7 @@ constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NQ>
-__global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, const float* __restrict__ q,
+__global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps) {
@@ -175,9 +181,19 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, const fl
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     const bool ok = j < rows_per_stream;
-    const float* qp = q + (long)(row0 + (ok ? j : 0)) * d + h * 64 + c8 * 8;
+    const long off = (long)(row0 + (ok ? j : 0)) * d + h * 64 + c8 * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qr[j][e] = ok ? qp[e] * 0.125f : 0.f;
+    for (int e = 0; e < 8; ++e) qr[j][e] = (ok && q.bias) ? q.bias[h * 64 + c8 * 8 + e] : 0.f;
+    for (int sp = 0; sp < q.nsplit; ++sp) {
+      const float4* qp = reinterpret_cast<const float4*>(q.ptr + (long)sp * q.stride + off);
+      const float4 a = qp[0], b2 = qp[1];
+      if (ok) {
+        qr[j][0] += a.x; qr[j][1] += a.y; qr[j][2] += a.z; qr[j][3] += a.w;
+        qr[j][4] += b2.x; qr[j][5] += b2.y; qr[j][6] += b2.z; qr[j][7] += b2.w;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qr[j][e] *= 0.125f;
   }
   int stage = 0;
   uint32_t phase = 0;
@@ -400,7 +416,7 @@ int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
 }
 
 template <int NQ>
-static void launch_cross(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
+static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
                          long slot_stride, const CrossAttnWorkspace& ws, int B, int rows_per_stream, int H, int d, int nsplit) {
   const int cps = (XA_NCHUNK + nsplit - 1) / nsplit;
   const int smem = xa_smem_bytes(cps, NQ);
@@ -418,7 +434,7 @@ void attention_prime() {
   WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
 }
 
-void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
+void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit) {
   WL_CHECK(rows_per_stream >= 1 && rows_per_stream <= MAX_ROWS_PER_STREAM, WL_ERR_ARG, "rows per stream %d", rows_per_stream);

@@ -45,14 +45,7 @@ void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int 
 // handful of rows, where a long unrolled body costs more in instruction fetch than in arithmetic.
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ be, __half* __restrict__ y,
-                                                        float* __restrict__ y32, long rows, int d, float* __restrict__ zero_buf,
-                                                        long zero_n) {
-  // optional side job: clear the fp32 buffer the next split-K GEMM accumulates into
-  {
-    float4* z4 = reinterpret_cast<float4*>(zero_buf);
-    const long n4z = zero_n >> 2;
-    for (long i = blockIdx.x * 256L + threadIdx.x; i < n4z; i += (long)gridDim.x * 256) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+                                                        float* __restrict__ y32, long rows, int d) {
   const long row = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -97,27 +90,35 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-// Decode-step variant: one 128-thread block per row (<= 3 float4 per thread) -- a few dozen instructions, so the
-// ~100 launches per decode step are not dominated by instruction fetch.  Extra blocks only clear `zero_buf`.
-__global__ void __launch_bounds__(128) layernorm_small_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                              const float* __restrict__ be, __half* __restrict__ y,
-                                                              long rows, int d, float* __restrict__ zero_buf, long zero_n) {
-  {
-    float4* z4 = reinterpret_cast<float4*>(zero_buf);
-    const long n4z = zero_n >> 2;
-    for (long i = blockIdx.x * 128L + threadIdx.x; i < n4z; i += (long)gridDim.x * 128) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+// Decode-step variant: one 128-thread block per row (<= 3 float4 per thread), a few dozen instructions -- the
+// ~100 launches per decode step must not be dominated by instruction fetch.  It also folds in the residual
+// update that the preceding split-K GEMM left as partial sums: x += bias + sum_s partial_s, in a fixed order.
+__global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict__ x, PartialSrc upd, const float* __restrict__ g,
+                                                               const float* __restrict__ be, __half* __restrict__ y, int d) {
   const long row = blockIdx.x;
-  if (row >= rows) return;
   __shared__ float red[8];
   const int tid = threadIdx.x, n4 = d >> 2;
-  const float4* x4 = reinterpret_cast<const float4*>(x + row * d);
+  float4* x4 = reinterpret_cast<float4*>(x + row * d);
   float4 v[3];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = i * 128 + tid;
-    v[i] = c < n4 ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n4) {
+      v[i] = x4[c];
+      if (upd.nsplit > 0) {
+        if (upd.bias) {
+          const float4 b = reinterpret_cast<const float4*>(upd.bias)[c];
+          v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+        }
+        for (int s = 0; s < upd.nsplit; ++s) {
+          const float4 p = reinterpret_cast<const float4*>(upd.ptr + (long)s * upd.stride + row * d)[c];
+          v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+        }
+        x4[c] = v[i];
+      }
+    }
     sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   sum = warp_sum(sum);
@@ -151,36 +152,42 @@ __global__ void __launch_bounds__(128) layernorm_small_kernel(const float* __res
   }
 }
 
+void layernorm_update_rows(cudaStream_t st, float* x, const PartialSrc& upd, const float* gamma, const float* beta, __half* y,
+                           int rows, int d) {
+  WL_CHECK(d <= 1536 && d % 4 == 0, WL_ERR_ARG, "layernorm_update: unsupported width %d", d);
+  layernorm_update_kernel<<<rows, 128, 0, st>>>(x, upd, gamma, beta, y, d);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32, long rows,
-                    int d, float* zero_buf, long zero_n) {
-  WL_CHECK(d <= 1280 && d % 4 == 0 && zero_n % 4 == 0, WL_ERR_ARG, "layernorm: unsupported width %d", d);
-  if (rows <= 1024 && y && !y32) {
-    int grid = (int)rows;
-    if (zero_buf && zero_n > 0) grid = std::max(grid, std::min(296, cdiv(zero_n, 128 * 16)));
-    layernorm_small_kernel<<<grid, 128, 0, st>>>(x, gamma, beta, y, rows, d, zero_buf, zero_buf ? zero_n : 0);
-    WL_CUDA(cudaGetLastError());
-    note_launch(1);
-    return;
-  }
-  int grid = cdiv(rows, 8);
-  if (zero_buf && zero_n > 0) grid = std::max(grid, std::min(148, cdiv(zero_n, 256 * 16)));
-  layernorm_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d, zero_buf, zero_buf ? zero_n : 0);
+                    int d) {
+  WL_CHECK(d <= 1280 && d % 4 == 0, WL_ERR_ARG, "layernorm: unsupported width %d", d);
+  const int grid = cdiv(rows, 8);
+  layernorm_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, y, y32, rows, d);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }
 
 // ---------------------------------------------------------------------------- gelu_cast
-__global__ void gelu_cast_kernel(const float* __restrict__ in, __half* __restrict__ out, long n) {
-  const long i = (blockIdx.x * 256L + threadIdx.x) * 4;
-  if (i >= n) return;
-  const float4 v = *reinterpret_cast<const float4*>(in + i);
+__global__ void gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int rows, int cols) {
+  const long i4 = blockIdx.x * 256L + threadIdx.x;          // float4 index
+  const int c4n = cols >> 2;
+  if (i4 >= (long)rows * c4n) return;
+  const int c = (int)(i4 % c4n);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in.bias) v = reinterpret_cast<const float4*>(in.bias)[c];
+  for (int s = 0; s < in.nsplit; ++s) {
+    const float4 p = reinterpret_cast<const float4*>(in.ptr + (long)s * in.stride)[i4];
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+  }
   __align__(8) __half2 h[2] = {__floats2half2_rn(gelu_erf(v.x), gelu_erf(v.y)), __floats2half2_rn(gelu_erf(v.z), gelu_erf(v.w))};
-  *reinterpret_cast<uint2*>(out + i) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(out + 4 * i4) = *reinterpret_cast<const uint2*>(h);
 }
 
-void gelu_cast(cudaStream_t st, const float* in, __half* out, long n) {
-  WL_CHECK(n % 4 == 0, WL_ERR_ARG, "gelu_cast: n must be a multiple of 4");
-  gelu_cast_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(in, out, n);
+void gelu_cast(cudaStream_t st, const PartialSrc& in, __half* out, int rows, int cols) {
+  WL_CHECK(cols % 4 == 0, WL_ERR_ARG, "gelu_cast: cols must be a multiple of 4");
+  gelu_cast_kernel<<<cdiv((long)rows * cols / 4, 256), 256, 0, st>>>(in, out, rows, cols);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

@@ -81,7 +81,7 @@ struct wl_ctx {
   std::vector<int> slot_free;
   std::vector<char> slot_used;
   // decoder workspaces
-  float *dx, *dqkv, *dqc, *dh32, *logits;
+  float *dx, *part1, *part2, *logits;
   __half *dxn, *datt, *dh, *kcache, *vcache;
   long cache_row_stride, cache_layer_stride;
   CrossAttnWorkspace xws;
@@ -392,9 +392,9 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   // ---- decoder workspaces
   const size_t R = c->Rm, Rp = (R + 15) / 16 * 16;
   c->dx = dalloc<float>(c, R * d);
-  c->dqkv = dalloc<float>(c, R * 3 * d);
-  c->dqc = dalloc<float>(c, R * d);
-  c->dh32 = dalloc<float>(c, R * ff);
+  // split-K partial sums: up to 16 K ranges of a d-wide output, 4 of the 3d-wide QKV, 3 of the 4d-wide MLP
+  c->part1 = dalloc<float>(c, R * 16 * (size_t)d + R * 4 * (size_t)ff);
+  c->part2 = dalloc<float>(c, R * 16 * (size_t)d);
   c->logits = dalloc<float>(c, R * c->Vld);
   c->dxn = dalloc<__half>(c, Rp * d);
   c->datt = dalloc<__half>(c, Rp * d);
@@ -656,44 +656,47 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     gemm_tn(st, opnd(W, n_out, K, K), opnd(X, R, K, K), n_out, R, K, e);
   };
   static const bool splitk = [] { const char* e = getenv("WLB200_SPLITK"); return e ? atoi(e) != 0 : true; }();
-  // Decode GEMMs are weight-streaming (M = out features, N = rows): split K over all SMs and let the partial
-  // sums accumulate atomically into fp32 buffers that already hold the residual (x) or zeros (cleared by the
-  // preceding LayerNorm launch).
-  auto acc_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* out, int ldn, const float* bias) {
+  // Decode GEMMs are weight-streaming (M = out features, N = rows <= 256): K is split over enough CTAs to fill the
+  // SMs; every K range stores its raw fp32 partial sum and the CONSUMER (LayerNorm, attention, GELU) adds the
+  // ranges and the bias in a fixed order -- no atomics, bit-reproducible, and no separate reduction kernel.
+  // part1 holds activations (qkv, q_cross, fc1), part2 the residual updates (out-proj, fc2) until the next LayerNorm.
+  auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias) -> PartialSrc {
     GemmEpilogue e;
-    e.out = out; e.out_f32 = 1; e.ldn = ldn; e.bias = bias;
-    if (splitk) e.accumulate = 1;
-    else if (out == c->dx) { e.resid = c->dx; e.rldm = 1; e.rldn = ldn; }
-    swap_gemm(W, n_out, K, X, e);
+    e.out = buf; e.out_f32 = 1; e.ldn = n_out; e.ldm = 1;
+    PartialSrc ps;
+    ps.ptr = buf; ps.bias = bias; ps.stride = (long)c->Rm * n_out;
+    if (splitk) {
+      ps.nsplit = gemm_split_plan(n_out, R, K);
+      e.partials = ps.nsplit; e.part_stride = ps.stride;
+    } else {
+      ps.nsplit = 1;   // single pass, bias still added by the consumer
+    }
+    gemm_tn(st, opnd(W, n_out, K, K), opnd(X, R, K, K), n_out, R, K, e);
+    return ps;
   };
+  PartialSrc pending;   // residual update not yet folded into x
   for (int l = 0; l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    layernorm_rows(st, c->dx, L.ln1_g, L.ln1_b, c->dxn, nullptr, R, d, splitk ? c->dqkv : nullptr, splitk ? (long)R * 3 * d : 0);
-    acc_gemm(L.w_qkv, 3 * d, d, c->dxn, c->dqkv, 3 * d, L.b_qkv);
-    decoder_self_attn(st, s, c->dqkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
+    layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv);
+    decoder_self_attn(st, s, qkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
-    acc_gemm(L.w_o, d, d, c->datt, c->dx, d, L.b_o);
-    layernorm_rows(st, c->dx, L.ln2_g, L.ln2_b, c->dxn, nullptr, R, d, splitk ? c->dqc : nullptr, splitk ? (long)R * d : 0);
-    acc_gemm(L.w_qc, d, d, c->dxn, c->dqc, d, L.b_qc);
+    pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o);
+    layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
+    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc);
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
-    decoder_cross_attn(st, s, c->dqc, c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz, c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz,
+    decoder_cross_attn(st, s, qc, c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz, c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz,
                        slot_sz, ws, c->datt, B, Kr, H, d, nsplit);
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
-    acc_gemm(L.w_oc, d, d, c->datt, c->dx, d, L.b_oc);
-    layernorm_rows(st, c->dx, L.ln3_g, L.ln3_b, c->dxn, nullptr, R, d, splitk ? c->dh32 : nullptr, splitk ? (long)R * ff : 0);
-    if (splitk) {
-      acc_gemm(L.w_fc1, ff, d, c->dxn, c->dh32, ff, L.b_fc1);
-      gelu_cast(st, c->dh32, c->dh, (long)R * ff);
-    } else {
-      GemmEpilogue e;
-      e.out = c->dh; e.out_f32 = 0; e.ldn = ff; e.bias = L.b_fc1; e.gelu = 1;
-      swap_gemm(L.w_fc1, ff, d, c->dxn, e);
-    }
-    acc_gemm(L.w_fc2, d, ff, c->dh, c->dx, d, L.b_fc2);
+    pending = part_gemm(L.w_oc, d, d, c->datt, c->part2, L.b_oc);
+    layernorm_update_rows(st, c->dx, pending, L.ln3_g, L.ln3_b, c->dxn, R, d);
+    const PartialSrc h1 = part_gemm(L.w_fc1, ff, d, c->dxn, c->part1, L.b_fc1);
+    gelu_cast(st, h1, c->dh, R, ff);
+    pending = part_gemm(L.w_fc2, d, ff, c->dh, c->part2, L.b_fc2);
   }
-  layernorm_rows(st, c->dx, c->lnf_g, c->lnf_b, c->dxn, nullptr, R, d);
+  layernorm_update_rows(st, c->dx, pending, c->lnf_g, c->lnf_b, c->dxn, R, d);
   {
     GemmEpilogue e;
     e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;

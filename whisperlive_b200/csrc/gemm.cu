@@ -37,25 +37,21 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 // Epilogue kinds are compile-time so that every kernel instantiation carries exactly one, compact epilogue: the
 // decode-step GEMMs run ~200 times per step on a few CTAs each, where instruction fetch of a fat multi-path
 // epilogue costs more than its arithmetic.
-enum EpiKind : int { EPI_ROW = 0, EPI_COL = 1, EPI_ACCUM = 2, EPI_HEADSPLIT = 3 };
+enum EpiKind : int { EPI_ROW = 0, EPI_COL = 1, EPI_PART = 2, EPI_HEADSPLIT = 3 };
 
 template <int cnt, int KIND>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2,
                                                int split = 0) {
   const GemmEpilogue& e = p.e;
   if (m >= p.M) return;
-  if constexpr (KIND == EPI_ACCUM) {
-    // split-K: out (fp32, already holding the residual or zeros) += partial (+ bias from split 0)
-    const long ob = m * e.ldm;
-    const float bm0 = (split == 0 && e.bias && e.bias_on_m) ? e.bias[m] : 0.f;
+  if constexpr (KIND == EPI_PART) {
+    // split-K: K range `split` stores its raw fp32 partial sum; whoever consumes the result adds the ranges
+    // (and the bias) in a fixed order -- no atomics, bit-reproducible.
+    float* dst = (float*)e.out + (long)split * e.part_stride + m * e.ldm;
 #pragma unroll
     for (int i = 0; i < cnt; ++i) {
       const int n = n0 + i;
-      if (n < p.N) {
-        float x = __uint_as_float(v[i]) + bm0;
-        if (split == 0 && e.bias && !e.bias_on_m) x += e.bias[n];
-        atomicAdd((float*)e.out + ob + (long)n * e.ldn, x);
-      }
+      if (n < p.N) dst[(long)n * e.ldn] = __uint_as_float(v[i]);
     }
     return;
   }
@@ -209,10 +205,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
-        const int z = KIND == EPI_ACCUM ? 0 : zz, split = KIND == EPI_ACCUM ? zz : 0;
+        const int z = KIND == EPI_PART ? 0 : zz, split = KIND == EPI_PART ? zz : 0;
         const int i1 = z % p.zn1, i2 = z / p.zn1;
-        const int kb0 = KIND == EPI_ACCUM ? split * p.kb_per_split : 0;
-        const int num_kb = KIND == EPI_ACCUM ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        const int kb0 = KIND == EPI_PART ? split * p.kb_per_split : 0;
+        const int num_kb = KIND == EPI_PART ? min(p.kb_per_split, total_kb - kb0) : total_kb;
         const int a1 = p.a_batched ? i1 : 0, a2 = p.a_batched ? i2 : 0;
         const int b1 = p.b_batched ? i1 : 0, b2 = p.b_batched ? i2 : 0;
         const int ca1 = slot(p.a_pos, 1, tile_m * BM, a1, a2), ca2 = slot(p.a_pos, 2, tile_m * BM, a1, a2),
@@ -236,8 +232,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int zz = (t / tiles_m) / tiles_n;
-        const int kb0 = KIND == EPI_ACCUM ? zz * p.kb_per_split : 0;
-        const int num_kb = KIND == EPI_ACCUM ? min(p.kb_per_split, total_kb - kb0) : total_kb;
+        const int kb0 = KIND == EPI_PART ? zz * p.kb_per_split : 0;
+        const int num_kb = KIND == EPI_PART ? min(p.kb_per_split, total_kb - kb0) : total_kb;
         mbar_wait(&acc_empty[as], aphase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t acc = tmem_acc + as * ACC_COLS;
@@ -268,7 +264,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
-      const int z = KIND == EPI_ACCUM ? 0 : zz, split = KIND == EPI_ACCUM ? zz : 0;
+      const int z = KIND == EPI_PART ? 0 : zz, split = KIND == EPI_PART ? zz : 0;
       const int i1 = z % p.zn1, i2 = z / p.zn1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -413,7 +409,7 @@ static void prime_kind() {
 void gemm_prime() {
   prime_kind<EPI_ROW>();
   prime_kind<EPI_COL>();
-  prime_kind<EPI_ACCUM>();
+  prime_kind<EPI_PART>();
   prime_kind<EPI_HEADSPLIT>();
 }
 
@@ -465,6 +461,18 @@ static GemmKParams make_params(const GemmOperand& A, const GemmOperand& B, int M
   return p;
 }
 
+// Number of K ranges for a weight-streaming (swap-AB) GEMM so that tiles x ranges fills the SMs; always a value
+// gemm_tn accepts (every range non-empty).
+int gemm_split_plan(int M, int N, int K) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int bn = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
+  const int tiles = cdiv(N, bn) * cdiv(M, BM), total_kb = cdiv(K, BK);
+  int s = std::max(1, std::min(std::min(total_kb, 16), sms / std::max(1, tiles)));
+  const int kbs = cdiv(total_kb, s);
+  return cdiv(total_kb, kbs);
+}
+
 void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& epi) {
   static const int force_simt = env_int("WLB200_GEMM_SIMT", 0);
   if (force_simt) return gemm_tn_simt(stream, A, B, M, N, K, epi);
@@ -479,36 +487,20 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   else if (N >= 512 && M >= 512 && epi.ldn == 1) bn = 256;
   else bn = 128;
   if (epi.mode == GEMM_HEADSPLIT && bn < 64) bn = 64;
-  if (epi.accumulate) {
-    WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && epi.mode == GEMM_STORE, WL_ERR_ARG,
-             "gemm_tn: accumulate (split-K) needs a plain fp32 output");
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int tiles = cdiv(N, bn) * cdiv(M, BM), total_kb = cdiv(K, BK);
-    // Cost model (measured on B200): a CTA streams its share of the weights at ~100 GB/s (latency-bound TMA ring),
-    // and the fp32 atomics of the epilogue retire at ~1.3 cycles per element per SM.  More splits shorten the
-    // stream but multiply the atomics (M*N per split): pick the split count that minimises the larger of the two.
-    int splits = 1;
-    {
-      const int max_s = tiles >= sms ? 1 : std::min(total_kb, std::max(1, sms / tiles));
-      double best = 1e30;
-      for (int s = 1; s <= max_s; ++s) {
-        const int kbs = cdiv(total_kb, s);
-        const double t_stream = (double)kbs * BK * 2.0 * (BM + bn) / 100e9;
-        const double t_atomic = (double)M * N * cdiv(total_kb, kbs) * 1.3 / (sms * 1.9e9);
-        const double cost = std::max(t_stream, t_atomic) + 0.05e-6 * s;
-        if (cost < best) { best = cost; splits = s; }
-      }
-    }
+  if (epi.partials > 0) {
+    WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && !epi.bias && epi.mode == GEMM_STORE, WL_ERR_ARG,
+             "gemm_tn: split-K partial output must be plain fp32 without bias");
+    const int total_kb = cdiv(K, BK);
     p.accum = 1;
-    p.kb_per_split = cdiv(total_kb, splits);
+    p.kb_per_split = cdiv(total_kb, epi.partials);
     Z = cdiv(total_kb, p.kb_per_split);
+    WL_CHECK(Z == epi.partials, WL_ERR_ARG, "gemm_tn: %d K ranges cannot be formed from %d k-blocks (use gemm_split_plan)", epi.partials, total_kb);
   }
   const TmapInfo ia = get_tmap(A, BM), ib = get_tmap(B, bn);
   const CUtensorMap& ta = ia.tm;
   const CUtensorMap& tb = ib.tm;
   for (int i = 0; i < 3; ++i) { p.a_pos[i] = ia.pos[i]; p.b_pos[i] = ib.pos[i]; }
-  if (p.accum) launch_kind<EPI_ACCUM>(bn, stream, ta, tb, p, Z);
+  if (p.accum) launch_kind<EPI_PART>(bn, stream, ta, tb, p, Z);
   else if (epi.mode == GEMM_HEADSPLIT) launch_kind<EPI_HEADSPLIT>(bn, stream, ta, tb, p, Z);
   else if (p.vec_ok) launch_kind<EPI_ROW>(bn, stream, ta, tb, p, Z);
   else launch_kind<EPI_COL>(bn, stream, ta, tb, p, Z);
@@ -528,10 +520,9 @@ __global__ void gemm_tn_simt_kernel(GemmOperand A, GemmOperand B, GemmKParams p)
   const int kk = ka < kb ? ka : kb;
   for (int k = 0; k < kk; ++k) acc = fmaf(__half2float(a[k]), __half2float(b[k]), acc);
   uint32_t v[1] = {__float_as_uint(acc)};
-  if (p.e.accumulate) {  // same contract as the split-K path, single pass
-    float x = acc;
-    if (p.e.bias) x += p.e.bias[p.e.bias_on_m ? m : n];
-    ((float*)p.e.out)[m * p.e.ldm + n * p.e.ldn] += x;
+  if (p.e.partials > 0) {  // same contract as the split-K path: range 0 carries the sum, the others zero
+    for (int sp = 0; sp < p.e.partials; ++sp)
+      ((float*)p.e.out)[(long)sp * p.e.part_stride + m * p.e.ldm + n * p.e.ldn] = sp == 0 ? acc : 0.f;
     return;
   }
   GemmKParams q = p;

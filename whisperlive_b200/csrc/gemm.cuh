@@ -33,7 +33,8 @@ struct GemmEpilogue {
   int gelu = 0;              // exact erf GELU after bias
   const float* resid = nullptr;  // fp32 residual added last; same indexing scheme as out
   long rldm = 0, rldn = 1, rb1 = 0, rb2 = 0;
-  int accumulate = 0;        // split-K: out (fp32, pre-initialised) += A*B^T (+bias); atomics, order not deterministic
+  int partials = 0;          // >0: split K into `partials` ranges; range s stores its raw fp32 partial sum at
+  long part_stride = 0;      //     out + s*part_stride (no bias); the consumer adds them in order (deterministic)
   int mode = GEMM_STORE;
   // GEMM_HEADSPLIT parameters
   int hs_S = 0, hs_H = 0;
@@ -51,6 +52,7 @@ void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& 
                   const GemmEpilogue& epi);
 
 long gemm_launch_count();
+int gemm_split_plan(int M, int N, int K);
 
 // Tensor map over an operand view (dims sorted by stride) + the coordinate slots of (row, i1, i2).
 struct TmapInfo {

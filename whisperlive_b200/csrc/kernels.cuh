@@ -22,14 +22,26 @@ struct MelTables {
 void mel_forward(cudaStream_t st, const float* pcm, const long* pcm_off, float* out, const long* out_off, unsigned* gmax,
                  const MelTables& t, int B, int max_frames);
 
+// A value produced by a split-K GEMM: v(r, c) = bias[c] + sum_s ptr[s * stride + r * ld + c]  (fixed order).
+// nsplit == 1 with bias == nullptr is a plain buffer; nsplit == 0 means "nothing pending".
+struct PartialSrc {
+  const float* ptr = nullptr;
+  int nsplit = 0;
+  long stride = 0;
+  const float* bias = nullptr;
+};
+
 // ---------------------------------------------------------------------------- elementwise / normalisation
 // features f32 [B][n_mels][3000] -> fp16 [B][3002][n_mels] (rows 0 and 3001 are zero: conv padding)
 void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int n_mels);
 // y = LayerNorm(x) * gamma + beta ; x f32 [rows][d] -> y fp16 [rows][d] (and optionally f32 copy)
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32,
-                    long rows, int d, float* zero_buf = nullptr, long zero_n = 0);
-// out = fp16(gelu(in)), n elements (n % 4 == 0)
-void gelu_cast(cudaStream_t st, const float* in, __half* out, long n);
+                    long rows, int d);
+// decode step: x[r] += upd(r, :) (residual update pending from a split-K GEMM), then y = LayerNorm(x) as fp16
+void layernorm_update_rows(cudaStream_t st, float* x, const PartialSrc& upd, const float* gamma, const float* beta, __half* y,
+                           int rows, int d);
+// out[r][c] = fp16(gelu(in(r, c))), rows x cols (cols % 4 == 0)
+void gelu_cast(cudaStream_t st, const PartialSrc& in, __half* out, int rows, int cols);
 // scores f32 [rows][ld_in] (first n valid) -> softmax(scale * s) as fp16 [rows][ld_out], columns >= n zeroed
 void softmax_rows(cudaStream_t st, const float* s, __half* p, long rows, int n, int ld_in, int ld_out, float scale);
 
@@ -92,7 +104,7 @@ struct VocabIds {
 void decoder_embed(cudaStream_t st, const DecodeState& s, const __half* emb, const __half* pos_emb, float* x, int R, int d);
 
 // K10: self attention over the KV cache with beam indirection. qkv f32 [R][3d]; out fp16 [R][d].
-void decoder_self_attn(cudaStream_t st, const DecodeState& s, const float* qkv, __half* kcache, __half* vcache,
+void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
                        long cache_row_stride, __half* out, int R, int H, int d);
 
 // K11: cross attention of the rows of each stream over its persistent encoder K/V.
@@ -101,7 +113,7 @@ struct CrossAttnWorkspace {
   float* part;     // [B][H][nsplit][MAX_ROWS_PER_STREAM][66]  (m, l, o[64])
   float* probs;    // optional [R][H][1500] f32 attention probabilities (align mode) or nullptr
 };
-void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const float* q, const __half* kc, const __half* vc,
+void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit);
 int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream);
