@@ -114,8 +114,8 @@ int wl_test_gemm(wl_ctx* ctx, const uint16_t* a_f16, const uint16_t* b_f16, cons
                  int32_t K, int32_t batch, int32_t transposed_store, int32_t gelu, int32_t use_simt);
 /* device-resident timing of the GEMM kernel: C = A(MxK) * B(NxK)^T, `iters` launches between CUDA events;
  * bn = 0 picks the tile like the engine does. ms_out = average milliseconds per launch. */
-int wl_bench_gemm(wl_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t transposed_store,
-                  float* ms_out);
+int wl_bench_gemm(wl_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t flags,
+                  float* ms_out); /* flags: 1 transposed store, 2 bias, 4 GELU, 8 fp32 output + fp32 residual */
 /* launches of library kernels since wl_init (gpu_launches accounting in bench.py) */
 int64_t wl_kernel_launches(wl_ctx* ctx);
 /* time (ms, CUDA events on the library stream) of the last wl_mel / wl_encode / wl_generate device work */

@@ -27,6 +27,9 @@ def run(M, N, K, batch=1, iters=20, tr=0):
 print("# encoder shapes (large-v3, 8 streams: M = 12000)")
 for (M, N, K) in [(12000, 2560, 1280), (12000, 1280, 1280), (12000, 5120, 1280), (12000, 1280, 5120), (8192, 8192, 8192)]:
     run(M, N, K)
+print("# encoder epilogue variants at M=12000: flags 2=bias 4=gelu 8=f32+residual")
+for (N, K, fl) in [(2560, 1280, 2), (1280, 1280, 8 | 2), (5120, 1280, 2 | 4), (1280, 5120, 8 | 2)]:
+    run(12000, N, K, tr=fl)
 print("# attention shapes (per head batches)")
 run(1500, 1500, 64, batch=40)
 run(1500, 64, 1536, batch=40)

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSr
                                                         __half* __restrict__ vc, long row_stride, __half* __restrict__ out,
                                                         int H, int d) {
   const int r = blockIdx.y, h = blockIdx.x, tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (!s.active[r]) return;
   const int pos = s.pos[r];
   const int n = pos + 1;
@@ -26,9 +28,10 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSr
     const long off = (long)r * 3 * d + h * 64 + tid;
     float qv = 0.f, kv = 0.f, vv = 0.f;
     if (qkv.bias) { qv = qkv.bias[h * 64 + tid]; kv = qkv.bias[d + h * 64 + tid]; vv = qkv.bias[2 * d + h * 64 + tid]; }
+#pragma unroll 4
     for (int sp = 0; sp < qkv.nsplit; ++sp) {
       const float* row = qkv.ptr + (long)sp * qkv.stride + off;
-      qv += row[0]; kv += row[d]; vv += row[2 * d];
+      qv += __ldcg(row); kv += __ldcg(row + d); vv += __ldcg(row + 2 * d);
     }
     q[tid] = qv * 0.125f;
     knew[tid] = kv;
@@ -111,8 +114,7 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSr
 void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
                        long cache_row_stride, __half* out, int R, int H, int d) {
   dim3 grid(H, R);
-  self_attn_kernel<<<grid, 128, 0, st>>>(s, qkv, kcache, vcache, cache_row_stride, out, H, d);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(self_attn_kernel, grid, dim3(128), 0, st, s, qkv, kcache, vcache, cache_row_stride, out, H, d);
   note_launch(1);
 }
 
@@ -139,13 +141,12 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   uint64_t* empty = full + XA_STAGES;
 
   const int b = blockIdx.z, h = blockIdx.y, sp = blockIdx.x;
-  if (s.done[b]) return;
   const int c_begin = sp * cps;
   const int c_end = min(XA_NCHUNK, c_begin + cps);
   if (c_begin >= c_end) return;
   const int nchunks = c_end - c_begin;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const long head_off = (long)s.slot[b] * slot_stride + (long)h * S_ENC * 64;
+  pdl_trigger();
 
   if (tid == 0) {
     for (int i = 0; i < XA_STAGES; ++i) {
@@ -158,13 +159,27 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 
   if (warp == 4) {
     // ------------------------------------------------------------------ producer warp
+    // The encoder K/V of the slot were written long before this decode step: the first K chunks are requested
+    // before the dependency wait, i.e. while the q projection that precedes this kernel is still running.
     if (elect_one()) {
+      const long head_off = (long)s.slot[b] * slot_stride + (long)h * S_ENC * 64;
       int stage = 0;
       uint32_t phase = 0;
+      bool checked = false;
       for (int pass = 0; pass < 2; ++pass) {
         const __half* src = (pass == 0 ? kc : vc) + head_off;
         for (int c = c_begin; c < c_end; ++c) {
           const int nkeys = min(XA_CHUNK, S_ENC - c * XA_CHUNK);
+          if (!checked && (pass == 1 || c - c_begin == XA_STAGES)) {
+            // ring is full for the first time: from here on the consumers must be alive
+            checked = true;
+            pdl_wait();
+            if (s.done[b]) {   // stream already finished: drain the requested chunks, then leave
+              const int issued = pass == 1 ? nchunks : XA_STAGES;
+              for (int i = 0; i < issued; ++i) mbar_wait(&full[i], 0);
+              return;
+            }
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], nkeys * 128);
           bulk_load_1d(stage_buf + stage * XA_STAGE_BYTES, src + (long)c * XA_CHUNK * 64, nkeys * 128, &full[stage]);
@@ -175,25 +190,33 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     return;
   }
   // -------------------------------------------------------------------- consumer warps (128 threads)
+  pdl_wait();
+  if (s.done[b]) return;
   const int c8 = tid & 7, g = tid >> 3;
   const int row0 = b * rows_per_stream;
+  // q rows of this (stream, head): bias + split-K partial sums in range order, reduced cooperatively (coalesced,
+  // 4 ranges in flight) into shared memory, then each thread picks up its 8-wide slice of every row.
+  {
+    float* qs = ored;   // [NQ][64], reused as the output reduction buffer at the end
+    for (int idx = tid; idx < NQ * 64; idx += 128) {
+      const int j = idx >> 6, dd = idx & 63;
+      float a = 0.f;
+      if (j < rows_per_stream) {
+        a = q.bias ? __ldg(q.bias + h * 64 + dd) : 0.f;
+        const float* qp = q.ptr + (long)(row0 + j) * d + h * 64 + dd;
+#pragma unroll 4
+        for (int sq = 0; sq < q.nsplit; ++sq) a += __ldcg(qp + (long)sq * q.stride);
+      }
+      qs[idx] = a * 0.125f;
+    }
+  }
+  consumers_sync();
   float qr[NQ][8];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    const bool ok = j < rows_per_stream;
-    const long off = (long)(row0 + (ok ? j : 0)) * d + h * 64 + c8 * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) qr[j][e] = (ok && q.bias) ? q.bias[h * 64 + c8 * 8 + e] : 0.f;
-    for (int sp = 0; sp < q.nsplit; ++sp) {
-      const float4* qp = reinterpret_cast<const float4*>(q.ptr + (long)sp * q.stride + off);
-      const float4 a = qp[0], b2 = qp[1];
-      if (ok) {
-        qr[j][0] += a.x; qr[j][1] += a.y; qr[j][2] += a.z; qr[j][3] += a.w;
-        qr[j][4] += b2.x; qr[j][5] += b2.y; qr[j][6] += b2.z; qr[j][7] += b2.w;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) qr[j][e] *= 0.125f;
+    const float4 a = *reinterpret_cast<const float4*>(ored + j * 64 + c8 * 8), b2 = *reinterpret_cast<const float4*>(ored + j * 64 + c8 * 8 + 4);
+    qr[j][0] = a.x; qr[j][1] = a.y; qr[j][2] = a.z; qr[j][3] = a.w;
+    qr[j][4] = b2.x; qr[j][5] = b2.y; qr[j][6] = b2.z; qr[j][7] = b2.w;
   }
   int stage = 0;
   uint32_t phase = 0;
@@ -373,6 +396,8 @@ __global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict
                                           int rows_per_stream, int H, int d, int nsplit) {
   const int r = blockIdx.y, h = blockIdx.x, dd = threadIdx.x;
   const int b = r / rows_per_stream, j = r % rows_per_stream;
+  pdl_trigger();
+  pdl_wait();
   if (s.done[b]) return;
   const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
   float M = -INFINITY;
@@ -421,8 +446,7 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   const int cps = (XA_NCHUNK + nsplit - 1) / nsplit;
   const int smem = xa_smem_bytes(cps, NQ);
   dim3 grid(nsplit, H, B);
-  cross_attn_kernel<NQ><<<grid, 160, smem, st>>>(s, q, kc, vc, slot_stride, ws.part, ws.probs, rows_per_stream, H, d, nsplit, cps);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(cross_attn_kernel<NQ>, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, rows_per_stream, H, d, nsplit, cps);
   note_launch(1);
 }
 
@@ -444,8 +468,7 @@ void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc&
   else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
   else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
   dim3 grid(H, B * rows_per_stream);
-  cross_attn_combine_kernel<<<grid, 64, 0, st>>>(s, ws.part, out, rows_per_stream, H, d, nsplit);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(cross_attn_combine_kernel, grid, dim3(64), 0, st, s, ws.part, out, rows_per_stream, H, d, nsplit);
   note_launch(1);
 }
 

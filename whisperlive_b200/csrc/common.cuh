@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
+#include <utility>
 
 #define WL_OK 0
 #define WL_ERR_CUDA -1
@@ -44,7 +46,33 @@ struct Error {
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 void note_launch(int n);  // kernel launch accounting (misc.cu)
 
+// Launches issued while a PdlScope(true) is alive carry the programmatic-stream-serialization attribute (the decoder
+// step: ~420 short dependent kernels per token, whose launch ramps and weight prefetch overlap the predecessor's
+// tail).  WLB200_PDL=0 disables it.
+bool pdl_active();
+struct PdlScope {
+  explicit PdlScope(bool on);
+  ~PdlScope();
+  bool prev;
+};
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_active() ? 1 : 0;
+  WL_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 // ----------------------------------------------------------------------------------- generic
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -60,18 +88,29 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // GELU in its exact erf form, 0.5 x (1 + erf(x / sqrt 2)).  erf is evaluated with Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, i.e. fp32 rounding level) on two MUFU ops + 6 FMAs instead of libdevice erff: the
-// epilogue of the 4d-wide MLP GEMM evaluates it 61 M times per encoder layer pass.
+// (|error| <= 1.5e-7, i.e. fp32 rounding level): with p = poly(t) t exp(-z^2), t = 1 / (1 + 0.3275911 z),
+// z = |x| / sqrt 2, gelu(x) = max(x, 0) - |x| p / 2.  Two MUFU ops (rcp.approx, ex2.approx) + 11 FP32 ops and
+// no branches -- the epilogue of the 4d-wide MLP GEMM evaluates it 61 M times per encoder layer pass.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+  const float w = ax * 0.84932180028801904272f;   // sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^(-w^2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  return fmaxf(x, 0.f) - ax * (poly * t * e);
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; it must execute pdl_wait() before it touches anything
+// the predecessor wrote (weights and other long-lived data may be fetched earlier).  pdl_trigger() lets the
+// successor's CTAs be scheduled as soon as every CTA of this grid has issued it.  Both are no-ops for kernels
+// launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -98,29 +98,47 @@ __global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict
   const long row = blockIdx.x;
   __shared__ float red[8];
   const int tid = threadIdx.x, n4 = d >> 2;
+  pdl_trigger();
   float4* x4 = reinterpret_cast<float4*>(x + row * d);
   float4 v[3];
-  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {   // the bias is a weight: fetch it before waiting for the producer kernel
+    const int c = i * 128 + tid;
+    v[i] = (c < n4 && upd.nsplit > 0 && upd.bias) ? __ldg(reinterpret_cast<const float4*>(upd.bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = i * 128 + tid;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < n4) {
-      v[i] = x4[c];
-      if (upd.nsplit > 0) {
-        if (upd.bias) {
-          const float4 b = reinterpret_cast<const float4*>(upd.bias)[c];
-          v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
-        }
-        for (int s = 0; s < upd.nsplit; ++s) {
-          const float4 p = reinterpret_cast<const float4*>(upd.ptr + (long)s * upd.stride + row * d)[c];
+      const float4 a = x4[c];
+      v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+    }
+  }
+  if (upd.nsplit > 0) {
+    // K ranges are added in index order (bit-reproducible); the loads of 4 ranges x 3 columns are in flight together
+    const float4* p4 = reinterpret_cast<const float4*>(upd.ptr + row * d);
+    const long st4 = upd.stride >> 2;
+#pragma unroll 4
+    for (int s = 0; s < upd.nsplit; ++s) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = i * 128 + tid;
+        if (c < n4) {
+          const float4 p = __ldcg(p4 + s * st4 + c);
           v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
         }
-        x4[c] = v[i];
       }
     }
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = i * 128 + tid;
+      if (c < n4) x4[c] = v[i];
+    }
   }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   sum = warp_sum(sum);
   if ((tid & 31) == 0) red[tid >> 5] = sum;
   __syncthreads();
@@ -155,8 +173,8 @@ __global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict
 void layernorm_update_rows(cudaStream_t st, float* x, const PartialSrc& upd, const float* gamma, const float* beta, __half* y,
                            int rows, int d) {
   WL_CHECK(d <= 1536 && d % 4 == 0, WL_ERR_ARG, "layernorm_update: unsupported width %d", d);
-  layernorm_update_kernel<<<rows, 128, 0, st>>>(x, upd, gamma, beta, y, d);
-  WL_CUDA(cudaGetLastError());
+  WL_CHECK(upd.nsplit == 0 || upd.stride % 4 == 0, WL_ERR_ARG, "layernorm_update: partial stride must be a multiple of 4");
+  launch_kernel(layernorm_update_kernel, dim3(rows), dim3(128), 0, st, x, upd, gamma, beta, y, d);
   note_launch(1);
 }
 
@@ -173,12 +191,17 @@ void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const f
 __global__ void gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int rows, int cols) {
   const long i4 = blockIdx.x * 256L + threadIdx.x;          // float4 index
   const int c4n = cols >> 2;
+  pdl_trigger();
   if (i4 >= (long)rows * c4n) return;
   const int c = (int)(i4 % c4n);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in.bias) v = reinterpret_cast<const float4*>(in.bias)[c];
+  if (in.bias) v = __ldg(reinterpret_cast<const float4*>(in.bias) + c);
+  pdl_wait();
+  const float4* p4 = reinterpret_cast<const float4*>(in.ptr) + i4;
+  const long st4 = in.stride >> 2;
+#pragma unroll 4
   for (int s = 0; s < in.nsplit; ++s) {
-    const float4 p = reinterpret_cast<const float4*>(in.ptr + (long)s * in.stride)[i4];
+    const float4 p = __ldcg(p4 + s * st4);
     v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
   }
   __align__(8) __half2 h[2] = {__floats2half2_rn(gelu_erf(v.x), gelu_erf(v.y)), __floats2half2_rn(gelu_erf(v.z), gelu_erf(v.w))};
@@ -187,8 +210,8 @@ __global__ void gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int ro
 
 void gelu_cast(cudaStream_t st, const PartialSrc& in, __half* out, int rows, int cols) {
   WL_CHECK(cols % 4 == 0, WL_ERR_ARG, "gelu_cast: cols must be a multiple of 4");
-  gelu_cast_kernel<<<cdiv((long)rows * cols / 4, 256), 256, 0, st>>>(in, out, rows, cols);
-  WL_CUDA(cudaGetLastError());
+  WL_CHECK(in.stride % 4 == 0, WL_ERR_ARG, "gelu_cast: partial stride must be a multiple of 4");
+  launch_kernel(gelu_cast_kernel, dim3(cdiv((long)rows * cols / 4, 256)), dim3(256), 0, st, in, out, rows, cols);
   note_launch(1);
 }
 
@@ -235,6 +258,8 @@ void softmax_rows(cudaStream_t st, const float* s, __half* p, long rows, int n, 
 __global__ void decoder_embed_kernel(DecodeState s, const __half* __restrict__ emb, const __half* __restrict__ pos_emb,
                                      float* __restrict__ x, int d) {
   const int r = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (!s.active[r]) return;
   const int tok = s.tok_in[r], pos = s.pos[r];
   for (int c = threadIdx.x; c < d; c += blockDim.x)
@@ -243,8 +268,7 @@ __global__ void decoder_embed_kernel(DecodeState s, const __half* __restrict__ e
 }
 
 void decoder_embed(cudaStream_t st, const DecodeState& s, const __half* emb, const __half* pos_emb, float* x, int R, int d) {
-  decoder_embed_kernel<<<R, 128, 0, st>>>(s, emb, pos_emb, x, d);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(decoder_embed_kernel, dim3(R), dim3(128), 0, st, s, emb, pos_emb, x, d);
   note_launch(1);
 }
 

@@ -649,6 +649,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   cudaStream_t st = c->st;
   const DecodeState& s = c->ds;
   const long slot_sz = (long)S_ENC * d;
+  PdlScope pdl(true);   // every kernel of the step is launched as a programmatic dependent of its predecessor
   decoder_embed(st, s, c->emb, c->pos_dec, c->dx, R, d);
   auto swap_gemm = [&](const __half* W, int n_out, int K, const __half* X, GemmEpilogue e) {
     e.ldm = 1;
@@ -663,6 +664,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias) -> PartialSrc {
     GemmEpilogue e;
     e.out = buf; e.out_f32 = 1; e.ldn = n_out; e.ldm = 1;
+    e.a_static = 1;
     PartialSrc ps;
     ps.ptr = buf; ps.bias = bias; ps.stride = (long)c->Rm * n_out;
     if (splitk) {
@@ -701,6 +703,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     GemmEpilogue e;
     e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;
     e.ldm = 1;
+    e.a_static = 1;
     gemm_tn(st, opnd(c->emb, c->V, d, d), opnd(c->dxn, R, d, d), c->V, R, d, e);
   }
   search_rows(st, s, c->logits, so, vi, R);
@@ -1114,21 +1117,31 @@ extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_
   API_END(c)
 }
 
-extern "C" int wl_bench_gemm(wl_ctx* c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t transposed_store,
+extern "C" int wl_bench_gemm(wl_ctx* c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t flags,
                              float* ms_out) {
+  // flags: 1 transposed (swap-AB) store, 2 bias, 4 GELU, 8 fp32 output with fp32 residual (in place)
   API_BEGIN(c)
   WL_CHECK(ms_out && M > 0 && N > 0 && K > 0 && batch > 0 && iters > 0, WL_ERR_ARG, "wl_bench_gemm: bad arguments");
-  __half *da = nullptr, *db = nullptr, *dc = nullptr;
+  __half *da = nullptr, *db = nullptr;
+  void* dc = nullptr;
+  float* dbias = nullptr;
+  const bool tr = flags & 1, f32 = flags & 8;
   const size_t na = (size_t)batch * M * K, nb = (size_t)batch * N * K, nc = (size_t)batch * M * N;
   WL_CUDA(cudaMalloc((void**)&da, na * 2));
   WL_CUDA(cudaMalloc((void**)&db, nb * 2));
-  WL_CUDA(cudaMalloc((void**)&dc, nc * 2));
+  WL_CUDA(cudaMalloc(&dc, nc * (f32 ? 4 : 2)));
+  WL_CUDA(cudaMalloc((void**)&dbias, (size_t)std::max(M, N) * 4));
   WL_CUDA(cudaMemset(da, 0x11, na * 2));
   WL_CUDA(cudaMemset(db, 0x11, nb * 2));
+  WL_CUDA(cudaMemset(dc, 0, nc * (f32 ? 4 : 2)));
+  WL_CUDA(cudaMemset(dbias, 0, (size_t)std::max(M, N) * 4));
   GemmEpilogue e;
-  e.out = dc; e.out_f32 = 0;
-  if (transposed_store) { e.ldm = 1; e.ldn = M; } else { e.ldm = N; e.ldn = 1; }
+  e.out = dc; e.out_f32 = f32 ? 1 : 0;
+  if (tr) { e.ldm = 1; e.ldn = M; } else { e.ldm = N; e.ldn = 1; }
   e.ob1 = (long)M * N;
+  if (flags & 2) { e.bias = dbias; e.bias_on_m = tr ? 1 : 0; }
+  if (flags & 4) e.gelu = 1;
+  if (f32) { e.resid = (const float*)dc; e.rldm = e.ldm; e.rldn = e.ldn; e.rb1 = e.ob1; }
   try {
     GemmOperand A = opnd(da, M, K, K, batch, (long)M * K), Bo = opnd(db, N, K, K, batch, (long)N * K);
     for (int i = 0; i < 3; ++i) gemm_tn(c->st, A, Bo, M, N, K, e);
@@ -1140,9 +1153,9 @@ extern "C" int wl_bench_gemm(wl_ctx* c, int32_t M, int32_t N, int32_t K, int32_t
     WL_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_out = ms / iters;
   } catch (...) {
-    cudaFree(da); cudaFree(db); cudaFree(dc);
+    cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dbias);
     throw;
   }
-  cudaFree(da); cudaFree(db); cudaFree(dc);
+  cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dbias);
   API_END(c)
 }

@@ -41,7 +41,7 @@ enum EpiKind : int { EPI_ROW = 0, EPI_COL = 1, EPI_PART = 2, EPI_HEADSPLIT = 3 }
 
 template <int cnt, int KIND>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int n0, const uint32_t (&v)[cnt], int i1, int i2,
-                                               int split = 0) {
+                                               int split = 0, const float4* rpre = nullptr) {
   const GemmEpilogue& e = p.e;
   if (m >= p.M) return;
   if constexpr (KIND == EPI_PART) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
       }
       if (e.resid) {
         const float* r = e.resid + rbase + n;
-        const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+        const float4 r0 = rpre ? rpre[i / 4] : *reinterpret_cast<const float4*>(r), r1 = rpre ? rpre[i / 4 + 1] : *reinterpret_cast<const float4*>(r + 4);
         x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
         x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
       }
@@ -170,6 +170,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int total_tiles = tiles_m * tiles_n * p.nz;
   const int total_kb = (p.K + BK - 1) / BK;
+  pdl_trigger();
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -199,6 +200,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      bool first = true;
       // coordinate slot s (1..3) of a tensor map holds whichever of (row, i1, i2) was sorted there
       auto slot = [](const int (&pos)[3], int s, int row, int j1, int j2) {
         return pos[0] == s ? row : (pos[1] == s ? j1 : (pos[2] == s ? j2 : 0));
@@ -215,12 +217,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   ca3 = slot(p.a_pos, 3, tile_m * BM, a1, a2);
         const int cb1 = slot(p.b_pos, 1, tile_n * BN, b1, b2), cb2 = slot(p.b_pos, 2, tile_n * BN, b1, b2),
                   cb3 = slot(p.b_pos, 3, tile_n * BN, b1, b2);
+        int pre = 0;
+        if (first) {
+          // First tile of this CTA.  When A is a weight matrix (decode: swap-AB, A = W) its k-blocks are requested
+          // BEFORE the dependency wait, so the weight stream overlaps the tail of the kernel that produces B.
+          if (p.e.a_static) {
+            pre = min(num_kb, STAGES);
+            for (int kb = 0; kb < pre; ++kb) {
+              mbar_expect_tx(&full[kb], A_STAGE_BYTES + B_STAGE_BYTES);
+              tma_load_4d(sA + kb * A_STAGE_BYTES, &tmA, &full[kb], (kb0 + kb) * BK, ca1, ca2, ca3);
+            }
+          }
+          pdl_wait();
+          first = false;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
           const int k0 = (kb0 + kb) * BK;
-          tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], k0, ca1, ca2, ca3);
-          tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
+          if (kb < pre) {
+            tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], k0, ca1, ca2, ca3);
+            tma_load_4d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], k0, cb1, cb2, cb3);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -262,6 +282,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_lo = ((warp - 4) >> 2) * HC;
     int as = 0;
     uint32_t aphase = 0;
+    pdl_wait();   // the residual / output buffers belong to the preceding kernels
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
       const int z = KIND == EPI_PART ? 0 : zz, split = KIND == EPI_PART ? zz : 0;
@@ -274,6 +295,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c = c_lo; c < c_lo + HC; c += 32) {
           uint32_t v[32];
+          // fp32 residual of this thread's 32 columns: requested before the accumulator read so that the 8 loads
+          // are in flight together (out may alias resid, which keeps the compiler from hoisting them itself)
+          float4 rr[8];
+          bool rr_ok = false;
+          if constexpr (KIND == EPI_ROW) {
+            const int n0 = tile_n * BN + c;
+            if (p.e.resid != nullptr && m < p.M && n0 + 32 <= p.N) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.e.resid + (long)i1 * p.e.rb1 + (long)i2 * p.e.rb2 + m * p.e.rldm + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rr[j] = r4[j];
+              rr_ok = true;
+            }
+          }
           tmem_ld_32x32(lane_addr + c, v);
           tmem_ld_wait();
           if (c + 32 >= c_lo + HC) {  // this warp's columns are in registers: hand the TMEM stage back before the stores
@@ -281,7 +315,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&acc_empty[as]);
           }
-          epilogue_chunk<32, KIND>(p, m, tile_n * BN + c, v, i1, i2, split);
+          if constexpr (KIND == EPI_ROW) {
+            if (rr_ok) epilogue_chunk<32, KIND>(p, m, tile_n * BN + c, v, i1, i2, split, rr);
+            else epilogue_chunk<32, KIND>(p, m, tile_n * BN + c, v, i1, i2, split);
+          } else {
+            epilogue_chunk<32, KIND>(p, m, tile_n * BN + c, v, i1, i2, split);
+          }
         }
       } else {
         uint32_t v[16];
@@ -386,8 +425,7 @@ static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
   q.nz = Z;
   const long tiles = (long)cdiv(p.N, BN) * cdiv(p.M, BM) * Z;
   const int grid = (int)std::min<long>(tiles, (long)sms * MIN_CTAS);
-  gemm_tn_kernel<BN, STAGES, MIN_CTAS, KIND><<<grid, 384, smem, stream>>>(ta, tb, q);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(gemm_tn_kernel<BN, STAGES, MIN_CTAS, KIND>, dim3(grid), dim3(384), (size_t)smem, stream, ta, tb, q);
   g_gemm_launches++;
 }
 
@@ -468,7 +506,7 @@ int gemm_split_plan(int M, int N, int K) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int bn = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
   const int tiles = cdiv(N, bn) * cdiv(M, BM), total_kb = cdiv(K, BK);
-  int s = std::max(1, std::min(std::min(total_kb, 16), sms / std::max(1, tiles)));
+  int s = std::max(1, std::min(std::min(total_kb, 8), sms / std::max(1, tiles)));
   const int kbs = cdiv(total_kb, s);
   return cdiv(total_kb, kbs);
 }

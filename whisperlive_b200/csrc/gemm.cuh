@@ -35,6 +35,8 @@ struct GemmEpilogue {
   long rldm = 0, rldn = 1, rb1 = 0, rb2 = 0;
   int partials = 0;          // >0: split K into `partials` ranges; range s stores its raw fp32 partial sum at
   long part_stride = 0;      //     out + s*part_stride (no bias); the consumer adds them in order (deterministic)
+  int a_static = 0;          // A is a weight matrix: under programmatic dependent launch its first k-blocks are
+                             //     fetched before waiting for the preceding kernel (which only produces B)
   int mode = GEMM_STORE;
   // GEMM_HEADSPLIT parameters
   int hs_S = 0, hs_H = 0;

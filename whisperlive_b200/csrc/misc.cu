@@ -1,5 +1,6 @@
 // Launch accounting, kernel attribute priming and the K14 attention-probability gather.
 #include <atomic>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -9,10 +10,21 @@ static std::atomic<long> g_other_launches{0};
 long other_launch_count() { return g_other_launches.load(); }
 void note_launch(int n) { g_other_launches += n; }
 
+static thread_local bool t_pdl = false;
+static bool pdl_env() {
+  static const bool on = [] { const char* e = getenv("WLB200_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+bool pdl_active() { return t_pdl; }
+PdlScope::PdlScope(bool on) : prev(t_pdl) { t_pdl = on && pdl_env(); }
+PdlScope::~PdlScope() { t_pdl = prev; }
+
 // copy the cross-attention probabilities of the alignment heads that live in `layer`
 __global__ void gather_align_kernel(DecodeState s, const float* __restrict__ probs, float* __restrict__ buf,
                                     const int* __restrict__ heads, int n_heads, int layer, int rows_per_stream, int H) {
   const int b = blockIdx.y, i = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (s.done[b] || heads[2 * i] != layer) return;
   const int h = heads[2 * i + 1], r = b * rows_per_stream, pos = s.pos[r];
   const float* src = probs + ((long)r * H + h) * S_ENC;
@@ -23,8 +35,7 @@ __global__ void gather_align_kernel(DecodeState s, const float* __restrict__ pro
 void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* probs, float* buf, const int* heads, int n_heads,
                         int layer, int B, int rows_per_stream, int H) {
   dim3 grid(n_heads, B);
-  gather_align_kernel<<<grid, 256, 0, st>>>(s, probs, buf, heads, n_heads, layer, rows_per_stream, H);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(gather_align_kernel, grid, dim3(256), 0, st, s, probs, buf, heads, n_heads, layer, rows_per_stream, H);
   note_launch(1);
 }
 

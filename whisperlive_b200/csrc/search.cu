@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
                                                                  VocabIds v) {
   const int r = blockIdx.x, tid = threadIdx.x;
   const int b = r / o.rows_per_stream;
+  pdl_trigger();
+  pdl_wait();
   if (!s.active[r] || s.done[b]) return;
   __shared__ float red[16];
   __shared__ float lkey[MAX_CAND][SR_THREADS];   // per-thread sorted lists, thread index fastest (no bank conflicts)
@@ -207,8 +209,7 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
 }
 
 void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, const SearchOpts& o, const VocabIds& v, int R) {
-  search_rows_kernel<<<R, SR_THREADS, 0, st>>>(s, logits, o, v);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(search_rows_kernel, dim3(R), dim3(SR_THREADS), 0, st, s, logits, o, v);
   note_launch(1);
 }
 
@@ -221,6 +222,8 @@ __device__ void finish_stream(DecodeState& s, int b, int Kr) {
 
 __global__ void __launch_bounds__(128) search_streams_kernel(DecodeState s, SearchOpts o, VocabIds v) {
   const int b = blockIdx.x, tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (s.done[b]) return;
   const int Kr = o.rows_per_stream, row0 = b * Kr;
   const int P = s.prompt_len[b], fed = s.fed[b];
@@ -420,8 +423,7 @@ __global__ void __launch_bounds__(128) search_streams_kernel(DecodeState s, Sear
 }
 
 void search_streams(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B) {
-  search_streams_kernel<<<B, 128, 0, st>>>(s, o, v);
-  WL_CUDA(cudaGetLastError());
+  launch_kernel(search_streams_kernel, dim3(B), dim3(128), 0, st, s, o, v);
   note_launch(1);
 }
 
