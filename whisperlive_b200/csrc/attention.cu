@@ -3,6 +3,7 @@
 //   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V,
 //       streamed HBM -> smem by a producer warp with cp.async.bulk + mbarrier ring, consumed by 4 warps.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -119,25 +120,65 @@ void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& 
 }
 
 // ============================================================================ K11 cross attention
+// Per (stream, head, key range): S = q K^T and O = P V on the warp-level tensor-core path (mma.sync m16n8k16,
+// fp16 operands, fp32 accumulate; N = 8 = the stream's beam rows).  The kernel is an HBM stream of the encoder
+// K/V (246 MB per layer at 32 streams) -- the arithmetic is ~0.1 GFLOP per CTA, so it stays on mma.sync rather
+// than tcgen05 (M = 128 x N >= 16 tiles + TMEM round trips buy nothing here); what matters is that the consumer
+// warps issue ~40 instructions per 16 KB chunk instead of ~400 on the CUDA-core path, which left the kernel
+// issue-bound at half of the HBM rate.
+//   * K/V chunks (128 keys x 64 dims, 16 KB contiguous) arrive by cp.async.bulk into a ring of XA_STAGES buffers.
+//     The pool stores every 128-byte key row with its 16-byte pieces XOR-swizzled by (key & 7) (written that way
+//     by the cross-KV GEMM epilogue), so ldmatrix reads the chunks bank-conflict free without a tensor map.
+//   * q is split into fp16 hi + lo parts (two MMAs): scores keep fp32-level accuracy in q; K is fp16 storage.
+//   * two passes over the key range (scores -> exact max/sum -> weights), so no online rescaling; P is fed to the
+//     second MMA as fp16, the row sum is taken over the same rounded values.
 constexpr int XA_CHUNK = 128;                 // keys per pipeline stage
-constexpr int XA_STAGES = 2;                  // x up to 4 CTAs per SM: 128 KB of K/V in flight per SM
+constexpr int XA_STAGES = 3;                  // x 3 CTAs per SM at beam <= 4: 144 KB of K/V in flight per SM
 constexpr int XA_STAGE_BYTES = XA_CHUNK * 128;  // 64 halves per key
 constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
+constexpr int XA_TAIL_KEYS = S_ENC - (XA_NCHUNK - 1) * XA_CHUNK;  // 92 keys in the last chunk
 
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D (16x8, f32) += A (16x16, f16, row) * B (16x8, f16, col)
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int NQ> struct XaCfg {
+  static constexpr int SW = NQ <= 2 ? 2 : NQ <= 4 ? 4 : 8;   // score columns kept per key (fp32)
+};
 
 template <int NQ>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps) {
+  constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
   uint8_t* base = xa_smem_raw + ((128u - (smem_u32(xa_smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS/STS)
-  uint8_t* stage_buf = base;                                           // XA_STAGES x 16 KB
-  float* S = reinterpret_cast<float*>(base + XA_STAGES * XA_STAGE_BYTES);  // [cps*128][8]
-  float* red = S + (long)cps * XA_CHUNK * 8;                            // [2][4][8] + o-reduce [4][NQ][64]
-  float* ored = red + 64;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ored + 4 * NQ * 64);
+  const int nk_cap = cps * XA_CHUNK;
+  const int ph_ld = nk_cap + 8;                                         // halves; +8 -> rows 16 B apart mod 128 B (conflict-free B fragments)
+  uint8_t* stage_buf = base;                                            // XA_STAGES x 16 KB
+  float* S = reinterpret_cast<float*>(base + XA_STAGES * XA_STAGE_BYTES);  // [cps*128][SW] scores, then exp()
+  __half* Ph = reinterpret_cast<__half*>(S + (long)nk_cap * SW);        // [NQ][ph_ld] weights for the P V MMA
+  float* red = reinterpret_cast<float*>(Ph + (long)NQ * ph_ld);         // [2][4][8]
+  float* ored = red + 64;                                               // [4][8][64] output reduction; first q staging [8][64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ored + 4 * 8 * 64);
   uint64_t* empty = full + XA_STAGES;
 
   const int b = blockIdx.z, h = blockIdx.y, sp = blockIdx.x;
@@ -145,7 +186,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int c_end = min(XA_NCHUNK, c_begin + cps);
   if (c_begin >= c_end) return;
   const int nchunks = c_end - c_begin;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_trigger();
 
   if (tid == 0) {
@@ -154,6 +195,16 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
       mbar_init(&empty[i], 4);
     }
     mbar_fence_init();
+  }
+  if (c_end == XA_NCHUNK) {
+    // the last chunk holds 92 keys: rows 92..127 of every ring buffer must be finite (their weights are exactly 0,
+    // but 0 x NaN would poison the P V product).  Later full chunks leave finite K/V values there.
+    constexpr int TAIL16 = (XA_CHUNK - XA_TAIL_KEYS) * 8;   // 16-byte pieces per buffer
+    for (int i = tid; i < XA_STAGES * TAIL16; i += 160) {
+      const int st = i / TAIL16, o = i % TAIL16;
+      *reinterpret_cast<uint4*>(stage_buf + st * XA_STAGE_BYTES + XA_TAIL_KEYS * 128 + o * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   __syncthreads();
 
@@ -192,107 +243,86 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   // -------------------------------------------------------------------- consumer warps (128 threads)
   pdl_wait();
   if (s.done[b]) return;
-  const int c8 = tid & 7, g = tid >> 3;
   const int row0 = b * rows_per_stream;
+  const int g = lane >> 2, tq = lane & 3;    // mma fragment coordinates: group (row / n index), thread-in-group
   // q rows of this (stream, head): bias + split-K partial sums in range order, reduced cooperatively (coalesced,
-  // 4 ranges in flight) into shared memory, then each thread picks up its 8-wide slice of every row.
-  {
-    float* qs = ored;   // [NQ][64], reused as the output reduction buffer at the end
-    for (int idx = tid; idx < NQ * 64; idx += 128) {
-      const int j = idx >> 6, dd = idx & 63;
-      float a = 0.f;
-      if (j < rows_per_stream) {
-        a = q.bias ? __ldg(q.bias + h * 64 + dd) : 0.f;
-        const float* qp = q.ptr + (long)(row0 + j) * d + h * 64 + dd;
+  // 4 ranges in flight) into shared memory as [8][64] fp32 (rows >= rows_per_stream are zero), pre-scaled by 1/8.
+  for (int idx = tid; idx < 8 * 64; idx += 128) {
+    const int j = idx >> 6, dd = idx & 63;
+    float a = 0.f;
+    if (j < rows_per_stream) {
+      a = q.bias ? __ldg(q.bias + h * 64 + dd) : 0.f;
+      const float* qp = q.ptr + (long)(row0 + j) * d + h * 64 + dd;
 #pragma unroll 4
-        for (int sq = 0; sq < q.nsplit; ++sq) a += __ldcg(qp + (long)sq * q.stride);
-      }
-      qs[idx] = a * 0.125f;
+      for (int sq = 0; sq < q.nsplit; ++sq) a += __ldcg(qp + (long)sq * q.stride);
     }
+    ored[idx] = a * 0.125f;
   }
   consumers_sync();
-  float qr[NQ][8];
+  // B fragments of q^T (k = dim, n = row): lane holds q[g][ks*16 + 2*tq + {0,1}] and [.. + 8], as hi + lo halves
+  uint32_t qh[4][2], ql[4][2];
 #pragma unroll
-  for (int j = 0; j < NQ; ++j) {
-    const float4 a = *reinterpret_cast<const float4*>(ored + j * 64 + c8 * 8), b2 = *reinterpret_cast<const float4*>(ored + j * 64 + c8 * 8 + 4);
-    qr[j][0] = a.x; qr[j][1] = a.y; qr[j][2] = a.z; qr[j][3] = a.w;
-    qr[j][4] = b2.x; qr[j][5] = b2.y; qr[j][6] = b2.z; qr[j][7] = b2.w;
-  }
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float2 v = *reinterpret_cast<const float2*>(ored + g * 64 + ks * 16 + r * 8 + 2 * tq);
+      const __half2 hi = __floats2half2_rn(v.x, v.y);
+      const float2 hf = __half22float2(hi);
+      qh[ks][r] = *reinterpret_cast<const uint32_t*>(&hi);
+      ql[ks][r] = pack_half2(v.x - hf.x, v.y - hf.y);
+    }
+  consumers_sync();   // ored is reused at the end
+
   int stage = 0;
   uint32_t phase = 0;
-  // pass 1: scores -> S[key][j]
+  // ---- pass 1: scores.  Warp w owns keys [32w, 32w+32) of every chunk: 2 m-tiles x 4 k-steps.
+  const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8;   // ldmatrix: row this lane addresses inside a 16-row tile
   for (int ci = 0; ci < nchunks; ++ci) {
     const int nkeys = min(XA_CHUNK, S_ENC - (c_begin + ci) * XA_CHUNK);
     mbar_wait(&full[stage], phase);
-    const uint8_t* buf = stage_buf + stage * XA_STAGE_BYTES;
-    float pr[8][NQ];
+    const uint32_t buf = smem_u32(stage_buf + stage * XA_STAGE_BYTES);
+    float sc[2][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = i * 16 + g;
-      float kf[8];
-      if (key < nkeys) {
-        const uint4 u = *reinterpret_cast<const uint4*>(buf + key * 128 + c8 * 16);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    for (int mt = 0; mt < 2; ++mt) {
+      sc[mt][0] = sc[mt][1] = sc[mt][2] = sc[mt][3] = 0.f;
+      const int key_l = warp * 32 + mt * 16 + ld_row;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
-          kf[2 * e] = f.x;
-          kf[2 * e + 1] = f.y;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) kf[e] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) a = fmaf(kf[e], qr[j][e], a);
-        pr[i][j] = a;
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        const int piece = ks * 2 + (lane >> 4);
+        ldmatrix_x4(a, buf + key_l * 128 + ((piece ^ (key_l & 7)) << 4));
+        mma_16816(sc[mt], a, qh[ks][0], qh[ks][1]);
+        mma_16816(sc[mt], a, ql[ks][0], ql[ks][1]);
       }
     }
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[stage]);  // K bytes are in registers now
+    if (lane == 0) mbar_arrive(&empty[stage]);  // K fragments are in registers now
     if (++stage == XA_STAGES) { stage = 0; phase ^= 1; }
-    // transpose-reduce over the 8 lanes that share a key: lane c8 ends with the full dot of key i == c8
+    if (2 * tq < SW) {
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-      float v4[4], v2[2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float lo = pr[i][j], hi = pr[i + 4][j];
-        const float send = (c8 & 4) ? lo : hi;
-        const float keep = (c8 & 4) ? hi : lo;
-        v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      for (int mt = 0; mt < 2; ++mt) {
+        const int k0 = warp * 32 + mt * 16 + g;
+        const float2 lo = k0 < nkeys ? make_float2(sc[mt][0], sc[mt][1]) : make_float2(-INFINITY, -INFINITY);
+        const float2 hi = k0 + 8 < nkeys ? make_float2(sc[mt][2], sc[mt][3]) : make_float2(-INFINITY, -INFINITY);
+        *reinterpret_cast<float2*>(S + ((long)ci * XA_CHUNK + k0) * SW + 2 * tq) = lo;
+        *reinterpret_cast<float2*>(S + ((long)ci * XA_CHUNK + k0 + 8) * SW + 2 * tq) = hi;
       }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float lo = v4[i], hi = v4[i + 2];
-        const float send = (c8 & 2) ? lo : hi;
-        const float keep = (c8 & 2) ? hi : lo;
-        v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-      const float send = (c8 & 1) ? v2[0] : v2[1];
-      const float keep = (c8 & 1) ? v2[1] : v2[0];
-      const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-      const int key = c8 * 16 + g;
-      S[((long)ci * XA_CHUNK + key) * 8 + j] = key < nkeys ? tot : -INFINITY;
     }
   }
   consumers_sync();
-  // softmax statistics over this CTA's key range
+  // ---- softmax statistics over this CTA's key range
   const int nk_pad = nchunks * XA_CHUNK;
   float mx[NQ], sm[NQ];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) mx[j] = -INFINITY;
   for (int k = tid; k < nk_pad; k += 128) {
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) mx[j] = fmaxf(mx[j], S[(long)k * 8 + j]);
+    for (int j = 0; j < NQ; ++j) mx[j] = fmaxf(mx[j], S[(long)k * SW + j]);
   }
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     mx[j] = warp_max(mx[j]);
-    if ((tid & 31) == 0) red[warp * 8 + j] = mx[j];
+    if (lane == 0) red[warp * 8 + j] = mx[j];
   }
   consumers_sync();
 #pragma unroll
@@ -303,15 +333,17 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   for (int k = tid; k < nk_pad; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      const float e = __expf(S[(long)k * 8 + j] - mx[j]);
-      S[(long)k * 8 + j] = e;
+      const __half eh = __float2half_rn(__expf(S[(long)k * SW + j] - mx[j]));
+      const float e = __half2float(eh);
+      Ph[(long)j * ph_ld + k] = eh;
+      S[(long)k * SW + j] = e;
       sm[j] += e;
     }
   }
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     sm[j] = warp_sum(sm[j]);
-    if ((tid & 31) == 0) red[32 + warp * 8 + j] = sm[j];
+    if (lane == 0) red[32 + warp * 8 + j] = sm[j];
   }
   consumers_sync();
 #pragma unroll
@@ -320,69 +352,56 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     for (int k = tid; k < S_ENC; k += 128) {
 #pragma unroll
       for (int j = 0; j < NQ; ++j)
-        if (j < rows_per_stream) probs[((long)(row0 + j) * H + h) * S_ENC + k] = S[(long)k * 8 + j] / sm[j];
+        if (j < rows_per_stream) probs[((long)(row0 + j) * H + h) * S_ENC + k] = S[(long)k * SW + j] / sm[j];
     }
   }
-  // pass 2: o[j][dd] += p[j][key] * V[key][dd]
-  float acc[NQ][8];
+  // ---- pass 2: O^T[dd][j] += V^T[dd][key] P^T[key][j].  Warp w owns keys [32w, 32w+32): 2 k-steps x 4 m-tiles of dd.
+  float o[4][4];
 #pragma unroll
-  for (int j = 0; j < NQ; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+  const int ldt_row = (lane & 7) + (lane >> 4) * 8;       // .trans tiles: matrices 2,3 are the second 8 keys
   for (int ci = 0; ci < nchunks; ++ci) {
-    const int nkeys = min(XA_CHUNK, S_ENC - (c_begin + ci) * XA_CHUNK);
     mbar_wait(&full[stage], phase);
-    const uint8_t* buf = stage_buf + stage * XA_STAGE_BYTES;
+    const uint32_t buf = smem_u32(stage_buf + stage * XA_STAGE_BYTES);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = i * 16 + g;
-      if (key < nkeys) {
-        const uint4 u = *reinterpret_cast<const uint4*>(buf + key * 128 + c8 * 16);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-        float vf[8];
+    for (int kk = 0; kk < 2; ++kk) {
+      const int kbase = warp * 32 + kk * 16;
+      uint32_t b0 = 0u, b1 = 0u;
+      if (g < NQ) {
+        const __half* pp = Ph + (long)g * ph_ld + ci * XA_CHUNK + kbase + 2 * tq;
+        b0 = *reinterpret_cast<const uint32_t*>(pp);
+        b1 = *reinterpret_cast<const uint32_t*>(pp + 8);
+      }
+      const int key_l = kbase + ldt_row;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
-          vf[2 * e] = f.x;
-          vf[2 * e + 1] = f.y;
-        }
-        const float* pk = S + ((long)ci * XA_CHUNK + key) * 8;
-        const float4 pa = *reinterpret_cast<const float4*>(pk), pb = *reinterpret_cast<const float4*>(pk + 4);
-        const float pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-        for (int j = 0; j < NQ; ++j)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(pw[j], vf[e], acc[j][e]);
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t a[4];
+        const int piece = mt * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4_trans(a, buf + key_l * 128 + ((piece ^ (key_l & 7)) << 4));
+        mma_16816(o[mt], a, b0, b1);
       }
     }
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
+    if (lane == 0) mbar_arrive(&empty[stage]);
     if (++stage == XA_STAGES) { stage = 0; phase ^= 1; }
   }
-  // reduce over the 16 key groups: 4 groups inside a warp (lane bits 3,4), then 4 warps through smem
+  // reduce the 4 warps (key quarters) through smem: lane holds O[j = 2tq + {0,1}][dd = mt*16 + g (+8)]
 #pragma unroll
-  for (int j = 0; j < NQ; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = acc[j][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      acc[j][e] = v;
-    }
-  if ((tid & 31) < 8) {
-#pragma unroll
-    for (int j = 0; j < NQ; ++j)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) ored[(warp * NQ + j) * 64 + c8 * 8 + e] = acc[j][e];
+  for (int mt = 0; mt < 4; ++mt) {
+    float* ob = ored + (warp * 8 + 2 * tq) * 64 + mt * 16 + g;
+    ob[0] = o[mt][0];
+    ob[64] = o[mt][1];
+    ob[8] = o[mt][2];
+    ob[64 + 8] = o[mt][3];
   }
   consumers_sync();
   float* dst = part + (((long)b * H + h) * nsplit + sp) * MAX_ROWS_PER_STREAM * 66;
   for (int idx = tid; idx < NQ * 64; idx += 128) {
     const int j = idx >> 6, dd = idx & 63;
     if (j < rows_per_stream) {
-      const float o = ored[(0 * NQ + j) * 64 + dd] + ored[(1 * NQ + j) * 64 + dd] + ored[(2 * NQ + j) * 64 + dd] +
-                      ored[(3 * NQ + j) * 64 + dd];
-      dst[j * 66 + 2 + dd] = o;
+      const float ov = ored[(0 * 8 + j) * 64 + dd] + ored[(1 * 8 + j) * 64 + dd] + ored[(2 * 8 + j) * 64 + dd] +
+                       ored[(3 * 8 + j) * 64 + dd];
+      dst[j * 66 + 2 + dd] = ov;
     }
   }
   if (tid < NQ && tid < rows_per_stream) {
@@ -412,26 +431,28 @@ __global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict
   out[(long)r * d + h * 64 + dd] = __float2half_rn(o / L);
 }
 
-static int xa_smem_bytes(int cps, int NQ) {
-  return 128 + XA_STAGES * XA_STAGE_BYTES + cps * XA_CHUNK * 8 * 4 + (64 + 4 * NQ * 64) * 4 + 2 * XA_STAGES * 8 + 64;
-}
 static int xa_template_nq(int rows_per_stream) {
   return rows_per_stream == 1 ? 1 : rows_per_stream == 2 ? 2 : rows_per_stream <= 4 ? 4 : rows_per_stream == 5 ? 5 : 8;
 }
+static int xa_smem_bytes(int cps, int NQ) {
+  const int sw = NQ <= 2 ? 2 : NQ <= 4 ? 4 : 8;
+  const int nk = cps * XA_CHUNK;
+  return 128 + XA_STAGES * XA_STAGE_BYTES + nk * sw * 4 + NQ * (nk + 8) * 2 + (64 + 4 * 8 * 64) * 4 + 2 * XA_STAGES * 8 + 64;
+}
 
 // Choose how many CTAs share one (stream, head): the grid should fill whole waves of resident CTAs
-// (occupancy is set by shared memory -- the score buffer shrinks with the split -- and by registers).
+// (occupancy is set by shared memory: the score / weight buffers shrink with the split).
 int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
+  static const int forced = [] { const char* e = getenv("WLB200_XA_NSPLIT"); return e ? atoi(e) : 0; }();
   const int NQ = xa_template_nq(rows_per_stream);
-  const int regs = NQ <= 2 ? 56 : NQ == 4 ? 96 : NQ == 5 ? 120 : 156;   // ptxas -v
-  const int occ_reg = std::max(1, 65536 / (regs * 160));
   int best_ns = 1;
   double best_eff = -1.0;
   for (int ns = 1; ns <= XA_NCHUNK; ++ns) {
     const int cps = (XA_NCHUNK + ns - 1) / ns;
     const int real = (XA_NCHUNK + cps - 1) / cps;
     if (real != ns) continue;
-    const int occ = std::max(1, std::min(occ_reg, (227 * 1024) / (xa_smem_bytes(cps, NQ) + 1024)));
+    if (forced == ns) return ns;
+    const int occ = std::max(1, std::min(12, (227 * 1024) / (xa_smem_bytes(cps, NQ) + 1024)));
     const long slots = (long)occ * num_sms, items = (long)B * H * ns;
     const long waves = (items + slots - 1) / slots;
     const double eff = (double)items / (double)(waves * slots) - 0.01 * ns;   // mild preference for fewer partials
@@ -451,11 +472,11 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
 }
 
 void attention_prime() {
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,

@@ -56,10 +56,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
     return;
   }
   if constexpr (KIND == EPI_HEADSPLIT && cnt >= 8) {
-    // m = (b, s), n = (h, dd); one thread writes cnt (<=32) consecutive dd of one head row
+    // m = (b, s), n = (h, dd); one thread writes cnt (<=32) consecutive dd of one head row.  The 16-byte pieces of a
+    // 128-byte key row are stored XOR-swizzled by (s & 7): the layout ldmatrix wants in the cross-attention kernel.
     const int b = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
     const int h = n0 >> 6, dd = n0 & 63;
-    __half* dst = (__half*)e.out + (long)e.hs_slots[b] * e.hs_slot_stride + ((long)h * e.hs_S + s) * 64 + dd;
+    __half* dst = (__half*)e.out + (long)e.hs_slots[b] * e.hs_slot_stride + ((long)h * e.hs_S + s) * 64;
 #pragma unroll
     for (int i = 0; i < cnt; i += 8) {
       if (n0 + i >= p.N) break;
@@ -73,7 +74,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
         }
         h2[j] = __floats2half2_rn(a, c);
       }
-      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(h2);
+      *reinterpret_cast<uint4*>(dst + ((((dd + i) >> 3) ^ (s & 7)) << 3)) = *reinterpret_cast<const uint4*>(h2);
     }
     return;
   }
@@ -569,7 +570,7 @@ __global__ void gemm_tn_simt_kernel(GemmOperand A, GemmOperand B, GemmKParams p)
     const GemmEpilogue& e = q.e;
     const int bb = (int)(m / e.hs_S), s = (int)(m % e.hs_S);
     float x = acc + (e.bias ? e.bias[n] : 0.f);
-    ((__half*)e.out)[(long)e.hs_slots[bb] * e.hs_slot_stride + ((long)(n >> 6) * e.hs_S + s) * 64 + (n & 63)] = __float2half_rn(x);
+    ((__half*)e.out)[(long)e.hs_slots[bb] * e.hs_slot_stride + ((long)(n >> 6) * e.hs_S + s) * 64 + (((((int)n & 63) >> 3) ^ (s & 7)) << 3) + (n & 7)] = __float2half_rn(x);
     return;
   }
   epilogue_chunk<1, EPI_COL>(q, m, (int)n, v, i1, i2);
