@@ -133,7 +133,7 @@ void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& 
 //   * two passes over the key range (scores -> exact max/sum -> weights), so no online rescaling; P is fed to the
 //     second MMA as fp16, the row sum is taken over the same rounded values.
 constexpr int XA_CHUNK = 128;                 // keys per pipeline stage
-constexpr int XA_STAGES = 3;                  // x 3 CTAs per SM at beam <= 4: 144 KB of K/V in flight per SM
+constexpr int XA_STAGES_DEFAULT = 3;          // x 3 CTAs per SM at beam <= 4: 144 KB of K/V in flight per SM
 constexpr int XA_STAGE_BYTES = XA_CHUNK * 128;  // 64 halves per key
 constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
 constexpr int XA_TAIL_KEYS = S_ENC - (XA_NCHUNK - 1) * XA_CHUNK;  // 92 keys in the last chunk
@@ -163,10 +163,11 @@ template <int NQ> struct XaCfg {
   static constexpr int SW = NQ <= 2 ? 2 : NQ <= 4 ? 4 : 8;   // score columns kept per key (fp32)
 };
 
-template <int NQ>
+template <int NQ, int XA_STAGES>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
+                                                         __half* __restrict__ out, int* __restrict__ counters,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps) {
   constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
@@ -330,14 +331,18 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     mx[j] = fmaxf(fmaxf(red[j], red[8 + j]), fmaxf(red[16 + j], red[24 + j]));
     sm[j] = 0.f;
   }
+  float sm32[NQ];   // exact fp32 sums: only the alignment probabilities use them
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) sm32[j] = 0.f;
   for (int k = tid; k < nk_pad; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      const __half eh = __float2half_rn(__expf(S[(long)k * SW + j] - mx[j]));
-      const float e = __half2float(eh);
+      const float e32 = __expf(S[(long)k * SW + j] - mx[j]);
+      const __half eh = __float2half_rn(e32);
       Ph[(long)j * ph_ld + k] = eh;
-      S[(long)k * SW + j] = e;
-      sm[j] += e;
+      S[(long)k * SW + j] = e32;
+      sm[j] += __half2float(eh);
+      sm32[j] += e32;
     }
   }
 #pragma unroll
@@ -349,10 +354,20 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 #pragma unroll
   for (int j = 0; j < NQ; ++j) sm[j] = red[32 + j] + red[40 + j] + red[48 + j] + red[56 + j];
   if (probs != nullptr && nsplit == 1) {
+    // K14 word alignment reads the attention probabilities themselves: exact fp32 exp / fp32 sum
+    consumers_sync();
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      sm32[j] = warp_sum(sm32[j]);
+      if (lane == 0) red[32 + warp * 8 + j] = sm32[j];
+    }
+    consumers_sync();
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) sm32[j] = red[32 + j] + red[40 + j] + red[48 + j] + red[56 + j];
     for (int k = tid; k < S_ENC; k += 128) {
 #pragma unroll
       for (int j = 0; j < NQ; ++j)
-        if (j < rows_per_stream) probs[((long)(row0 + j) * H + h) * S_ENC + k] = S[(long)k * SW + j] / sm[j];
+        if (j < rows_per_stream) probs[((long)(row0 + j) * H + h) * S_ENC + k] = S[(long)k * SW + j] / sm32[j];
     }
   }
   // ---- pass 2: O^T[dd][j] += V^T[dd][key] P^T[key][j].  Warp w owns keys [32w, 32w+32): 2 k-steps x 4 m-tiles of dd.
@@ -395,7 +410,22 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     ob[64 + 8] = o[mt][3];
   }
   consumers_sync();
-  float* dst = part + (((long)b * H + h) * nsplit + sp) * MAX_ROWS_PER_STREAM * 66;
+  if (nsplit == 1) {   // the whole key range was here: normalise and store the attention output directly
+    for (int idx = tid; idx < NQ * 64; idx += 128) {
+      const int j = idx >> 6, dd = idx & 63;
+      if (j < rows_per_stream) {
+        const float ov = ored[(0 * 8 + j) * 64 + dd] + ored[(1 * 8 + j) * 64 + dd] + ored[(2 * 8 + j) * 64 + dd] +
+                         ored[(3 * 8 + j) * 64 + dd];
+        float l = sm[0];
+#pragma unroll
+        for (int jj = 1; jj < NQ; ++jj) l = j == jj ? sm[jj] : l;
+        out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(ov / l);
+      }
+    }
+    return;
+  }
+  float* pbase = part + ((long)b * H + h) * nsplit * MAX_ROWS_PER_STREAM * 66;
+  float* dst = pbase + (long)sp * MAX_ROWS_PER_STREAM * 66;
   for (int idx = tid; idx < NQ * 64; idx += 128) {
     const int j = idx >> 6, dd = idx & 63;
     if (j < rows_per_stream) {
@@ -408,36 +438,48 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     dst[tid * 66 + 0] = mx[tid];
     dst[tid * 66 + 1] = sm[tid];
   }
-}
-
-// merge the nsplit partial softmaxes of every (row, head)
-__global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict__ part, __half* __restrict__ out,
-                                          int rows_per_stream, int H, int d, int nsplit) {
-  const int r = blockIdx.y, h = blockIdx.x, dd = threadIdx.x;
-  const int b = r / rows_per_stream, j = r % rows_per_stream;
-  pdl_trigger();
-  pdl_wait();
-  if (s.done[b]) return;
-  const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
-  float M = -INFINITY;
-  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, p[(long)sp * MAX_ROWS_PER_STREAM * 66]);
-  float L = 0.f, o = 0.f;
-  for (int sp = 0; sp < nsplit; ++sp) {
-    const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
-    const float w = __expf(ps[0] - M);
-    L += ps[1] * w;
-    o += ps[2 + dd] * w;
+  // The CTA that finishes a (stream, head) last merges its nsplit partial softmaxes (in key-range order, so the
+  // result does not depend on which CTA that is) -- no separate combine launch.
+  __threadfence();
+  consumers_sync();
+  if (tid == 0) red[0] = (atomicAdd(&counters[b * H + h], 1) == nsplit - 1) ? 1.f : 0.f;
+  consumers_sync();
+  if (red[0] == 0.f) return;
+  __threadfence();
+  if (tid == 0) counters[b * H + h] = 0;   // ready for the next launch
+  for (int idx = tid; idx < NQ * 64; idx += 128) {
+    const int j = idx >> 6, dd = idx & 63;
+    if (j < rows_per_stream) {
+      const float* pj = pbase + j * 66;
+      float M = -INFINITY;
+      for (int q2 = 0; q2 < nsplit; ++q2) M = fmaxf(M, __ldcg(pj + (long)q2 * MAX_ROWS_PER_STREAM * 66));
+      float L = 0.f, ov = 0.f;
+      for (int q2 = 0; q2 < nsplit; ++q2) {
+        const float* ps = pj + (long)q2 * MAX_ROWS_PER_STREAM * 66;
+        const float w = __expf(__ldcg(ps) - M);
+        L += __ldcg(ps + 1) * w;
+        ov += __ldcg(ps + 2 + dd) * w;
+      }
+      out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(ov / L);
+    }
   }
-  out[(long)r * d + h * 64 + dd] = __float2half_rn(o / L);
 }
 
 static int xa_template_nq(int rows_per_stream) {
   return rows_per_stream == 1 ? 1 : rows_per_stream == 2 ? 2 : rows_per_stream <= 4 ? 4 : rows_per_stream == 5 ? 5 : 8;
 }
+static int xa_stages() {
+  static const int st = [] {
+    const char* e = getenv("WLB200_XA_STAGES");
+    const int v = e ? atoi(e) : XA_STAGES_DEFAULT;
+    return v == 2 || v == 4 ? v : 3;
+  }();
+  return st;
+}
 static int xa_smem_bytes(int cps, int NQ) {
   const int sw = NQ <= 2 ? 2 : NQ <= 4 ? 4 : 8;
   const int nk = cps * XA_CHUNK;
-  return 128 + XA_STAGES * XA_STAGE_BYTES + nk * sw * 4 + NQ * (nk + 8) * 2 + (64 + 4 * 8 * 64) * 4 + 2 * XA_STAGES * 8 + 64;
+  return 128 + xa_stages() * XA_STAGE_BYTES + nk * sw * 4 + NQ * (nk + 8) * 2 + (64 + 4 * 8 * 64) * 4 + 2 * xa_stages() * 8 + 64;
 }
 
 // Choose how many CTAs share one (stream, head): the grid should fill whole waves of resident CTAs
@@ -445,8 +487,10 @@ static int xa_smem_bytes(int cps, int NQ) {
 int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
   static const int forced = [] { const char* e = getenv("WLB200_XA_NSPLIT"); return e ? atoi(e) : 0; }();
   const int NQ = xa_template_nq(rows_per_stream);
+  // cost of a split = waves of resident CTAs x (chunks per CTA + a fixed per-CTA cost of ~3 chunk times: q reduction,
+  // pipeline fill, the softmax pass between the two sweeps, partial write-out); ties go to fewer partials
   int best_ns = 1;
-  double best_eff = -1.0;
+  double best_cost = 1e30;
   for (int ns = 1; ns <= XA_NCHUNK; ++ns) {
     const int cps = (XA_NCHUNK + ns - 1) / ns;
     const int real = (XA_NCHUNK + cps - 1) / cps;
@@ -455,42 +499,48 @@ int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
     const int occ = std::max(1, std::min(12, (227 * 1024) / (xa_smem_bytes(cps, NQ) + 1024)));
     const long slots = (long)occ * num_sms, items = (long)B * H * ns;
     const long waves = (items + slots - 1) / slots;
-    const double eff = (double)items / (double)(waves * slots) - 0.01 * ns;   // mild preference for fewer partials
-    if (eff > best_eff) { best_eff = eff; best_ns = ns; }
+    const double cost = (double)waves * (cps + 3.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_ns = ns; }
   }
   return best_ns;
 }
 
 template <int NQ>
 static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
-                         long slot_stride, const CrossAttnWorkspace& ws, int B, int rows_per_stream, int H, int d, int nsplit) {
+                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H, int d,
+                         int nsplit) {
   const int cps = (XA_NCHUNK + nsplit - 1) / nsplit;
   const int smem = xa_smem_bytes(cps, NQ);
   dim3 grid(nsplit, H, B);
-  launch_kernel(cross_attn_kernel<NQ>, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, rows_per_stream, H, d, nsplit, cps);
+  const int stg = xa_stages();
+  auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, rows_per_stream, H, d, nsplit, cps);
   note_launch(1);
 }
 
+template <int NQ>
+static void prime_cross() {
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<NQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<NQ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<NQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
 void attention_prime() {
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  prime_cross<1>();
+  prime_cross<2>();
+  prime_cross<4>();
+  prime_cross<5>();
+  prime_cross<8>();
 }
 
 void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit) {
   WL_CHECK(rows_per_stream >= 1 && rows_per_stream <= MAX_ROWS_PER_STREAM, WL_ERR_ARG, "rows per stream %d", rows_per_stream);
-  if (rows_per_stream == 1) launch_cross<1>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
-  else if (rows_per_stream == 2) launch_cross<2>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
-  else if (rows_per_stream <= 4) launch_cross<4>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
-  else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
-  else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, B, rows_per_stream, H, d, nsplit);
-  dim3 grid(H, B * rows_per_stream);
-  launch_kernel(cross_attn_combine_kernel, grid, dim3(64), 0, st, s, ws.part, out, rows_per_stream, H, d, nsplit);
-  note_launch(1);
+  if (rows_per_stream == 1) launch_cross<1>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  else if (rows_per_stream == 2) launch_cross<2>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  else if (rows_per_stream <= 4) launch_cross<4>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
 }
 
 }  // namespace wl

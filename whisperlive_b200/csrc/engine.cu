@@ -405,6 +405,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
   c->xws.part = dalloc<float>(c, (size_t)c->Bm * H * 12 * MAX_ROWS_PER_STREAM * 66);
   c->xws.probs = nullptr;
+  c->xws.counters = dalloc<int>(c, (size_t)c->Bm * H);
   c->suppress_mask = dalloc<unsigned>(c, (V + 31) / 32 + 1);
   if (!c->align_heads.empty()) {
     c->align_heads_dev = dalloc<int>(c, c->align_heads.size());
