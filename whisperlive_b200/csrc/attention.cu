@@ -10,51 +10,67 @@
 namespace wl {
 
 // ============================================================================ K10 self attention
-__global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSrc qkv, __half* __restrict__ kc,
-                                                        __half* __restrict__ vc, long row_stride, __half* __restrict__ out,
-                                                        int H, int d) {
-  const int r = blockIdx.y, h = blockIdx.x, tid = threadIdx.x;
+// One WARP per (row, head): at most 448 cached positions x 64 dims is far too little work for a thread block, and
+// 2560 blocks (32 streams x beam 4 x 20 heads) would need several waves.  No block-level barriers: lanes own
+// positions for the scores (one 128-byte K row each), dims for the weighted V sum (coalesced 128-byte V rows).
+constexpr int SA_WARPS = 4;
+
+__global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s, PartialSrc qkv, __half* __restrict__ kc,
+                                                                 __half* __restrict__ vc, long row_stride,
+                                                                 __half* __restrict__ out, int H, int d, int R) {
+  __shared__ float qs[SA_WARPS][64];
+  __shared__ float sc_all[SA_WARPS][T_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * SA_WARPS + warp;
   pdl_trigger();
-  pdl_wait();
-  if (!s.active[r]) return;
+  if (item >= R * H) return;
+  const int r = item / H, h = item % H;
+  if (!s.active[r]) return;          // per-step state: written before this step's first kernel started
   const int pos = s.pos[r];
   const int n = pos + 1;
-  __shared__ float q[64], knew[64], vnew[64];
-  __shared__ float sc[T_MAX];
-  __shared__ float red[8];
-  __shared__ float opart[16][64];
-
-  if (tid < 64) {
-    // q / k / v of this (row, head): bias + the split-K partial sums, in order
-    const long off = (long)r * 3 * d + h * 64 + tid;
-    float qv = 0.f, kv = 0.f, vv = 0.f;
-    if (qkv.bias) { qv = qkv.bias[h * 64 + tid]; kv = qkv.bias[d + h * 64 + tid]; vv = qkv.bias[2 * d + h * 64 + tid]; }
+  float* q = qs[warp];
+  float* sc = sc_all[warp];
+  // q / k / v of this (row, head), dims 2*lane and 2*lane+1: bias + the split-K partial sums, in range order
+  const int c0 = h * 64 + 2 * lane;
+  float2 qv = make_float2(0.f, 0.f), kv = qv, vv = qv;
+  if (qkv.bias) {
+    qv = __ldg(reinterpret_cast<const float2*>(qkv.bias + c0));
+    kv = __ldg(reinterpret_cast<const float2*>(qkv.bias + d + c0));
+    vv = __ldg(reinterpret_cast<const float2*>(qkv.bias + 2 * d + c0));
+  }
+  pdl_wait();
+  {
+    const float* row = qkv.ptr + (long)r * 3 * d + c0;
 #pragma unroll 4
     for (int sp = 0; sp < qkv.nsplit; ++sp) {
-      const float* row = qkv.ptr + (long)sp * qkv.stride + off;
-      qv += __ldcg(row); kv += __ldcg(row + d); vv += __ldcg(row + 2 * d);
+      const float* p = row + (long)sp * qkv.stride;
+      const float2 a = __ldcg(reinterpret_cast<const float2*>(p)), b2 = __ldcg(reinterpret_cast<const float2*>(p + d)),
+                   c2 = __ldcg(reinterpret_cast<const float2*>(p + 2 * d));
+      qv.x += a.x; qv.y += a.y; kv.x += b2.x; kv.y += b2.y; vv.x += c2.x; vv.y += c2.y;
     }
-    q[tid] = qv * 0.125f;
-    knew[tid] = kv;
-    vnew[tid] = vv;
-    const long o = (long)r * row_stride + ((long)h * T_MAX + pos) * 64 + tid;
-    kc[o] = __float2half_rn(kv);
-    vc[o] = __float2half_rn(vv);
   }
-  __syncthreads();
+  qv.x *= 0.125f; qv.y *= 0.125f;
+  *reinterpret_cast<float2*>(q + 2 * lane) = qv;
+  {
+    const long o = (long)r * row_stride + ((long)h * T_MAX + pos) * 64 + 2 * lane;
+    *reinterpret_cast<__half2*>(kc + o) = __floats2half2_rn(kv.x, kv.y);
+    *reinterpret_cast<__half2*>(vc + o) = __floats2half2_rn(vv.x, vv.y);
+  }
+  const float dot_new = warp_sum(qv.x * kv.x + qv.y * kv.y);   // the new position uses the unrounded k (as before)
+  __syncwarp();
   const short* src = s.src + (long)r * T_MAX;
   float lmax = -INFINITY;
-  for (int p = tid; p < n; p += 128) {
-    float acc = 0.f;
-    if (p == pos) {
-#pragma unroll 8
-      for (int e = 0; e < 64; ++e) acc = fmaf(q[e], knew[e], acc);
-    } else {
+  for (int p = lane; p < n; p += 32) {
+    float acc = dot_new;
+    if (p != pos) {
       const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)src[p] * row_stride + ((long)h * T_MAX + p) * 64);
+      uint4 u[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) u[c] = kp[c];
+      acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint4 u = kp[c];
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u[c]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __half22float2(h2[e]);
@@ -66,56 +82,33 @@ __global__ void __launch_bounds__(128) self_attn_kernel(DecodeState s, PartialSr
     sc[p] = acc;
     lmax = fmaxf(lmax, acc);
   }
-  lmax = warp_max(lmax);
-  if ((tid & 31) == 0) red[tid >> 5] = lmax;
-  __syncthreads();
-  const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  const float mx = warp_max(lmax);
   float lsum = 0.f;
-  for (int p = tid; p < n; p += 128) {
+  for (int p = lane; p < n; p += 32) {
     const float e = __expf(sc[p] - mx);
     sc[p] = e;
     lsum += e;
   }
-  lsum = warp_sum(lsum);
-  if ((tid & 31) == 0) red[4 + (tid >> 5)] = lsum;
-  __syncthreads();
-  const float inv = 1.f / (red[4] + red[5] + red[6] + red[7]);
-
-  const int c8 = tid & 7, g = tid >> 3;
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int p = g; p < n; p += 16) {
+  const float inv = 1.f / warp_sum(lsum);
+  __syncwarp();
+  float2 acc = make_float2(0.f, 0.f);
+  const long hoff = (long)h * T_MAX * 64 + 2 * lane;
+#pragma unroll 4
+  for (int p = 0; p < pos; ++p) {
     const float w = sc[p];
-    if (p == pos) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, vnew[c8 * 8 + e], acc[e]);
-    } else {
-      const uint4 u = *reinterpret_cast<const uint4*>(vc + (long)src[p] * row_stride + ((long)h * T_MAX + p) * 64 + c8 * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h2[e]);
-        acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
-      }
-    }
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vc + (long)src[p] * row_stride + hoff + (long)p * 64));
+    acc.x = fmaf(w, f.x, acc.x);
+    acc.y = fmaf(w, f.y, acc.y);
   }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) opart[g][c8 * 8 + e] = acc[e];
-  __syncthreads();
-  if (tid < 64) {
-    float t = 0.f;
-#pragma unroll
-    for (int gg = 0; gg < 16; ++gg) t += opart[gg][tid];
-    out[(long)r * d + h * 64 + tid] = __float2half_rn(t * inv);
-  }
+  acc.x = fmaf(sc[pos], vv.x, acc.x);
+  acc.y = fmaf(sc[pos], vv.y, acc.y);
+  *reinterpret_cast<__half2*>(out + (long)r * d + c0) = __floats2half2_rn(acc.x * inv, acc.y * inv);
 }
 
 void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
                        long cache_row_stride, __half* out, int R, int H, int d) {
-  dim3 grid(H, R);
-  launch_kernel(self_attn_kernel, grid, dim3(128), 0, st, s, qkv, kcache, vcache, cache_row_stride, out, H, d);
+  launch_kernel(self_attn_kernel, dim3(cdiv((long)R * H, SA_WARPS)), dim3(SA_WARPS * 32), 0, st, s, qkv, kcache, vcache,
+                cache_row_stride, out, H, d, R);
   note_launch(1);
 }
 
@@ -137,6 +130,7 @@ constexpr int XA_STAGES_DEFAULT = 3;          // x 3 CTAs per SM at beam <= 4: 1
 constexpr int XA_STAGE_BYTES = XA_CHUNK * 128;  // 64 halves per key
 constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
 constexpr int XA_TAIL_KEYS = S_ENC - (XA_NCHUNK - 1) * XA_CHUNK;  // 92 keys in the last chunk
+constexpr int MAX_STREAMS_CAP = 256;          // streams per decode call the live list can hold
 
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -167,7 +161,7 @@ template <int NQ, int XA_STAGES>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
-                                                         __half* __restrict__ out, int* __restrict__ counters,
+                                                         __half* __restrict__ out, int* __restrict__ counters, int B,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps) {
   constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
@@ -182,12 +176,9 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   uint64_t* full = reinterpret_cast<uint64_t*>(ored + 4 * 8 * 64);
   uint64_t* empty = full + XA_STAGES;
 
-  const int b = blockIdx.z, h = blockIdx.y, sp = blockIdx.x;
-  const int c_begin = sp * cps;
-  const int c_end = min(XA_NCHUNK, c_begin + cps);
-  if (c_begin >= c_end) return;
-  const int nchunks = c_end - c_begin;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ int live[MAX_STREAMS_CAP];
+  __shared__ int n_live_sh;
   pdl_trigger();
 
   if (tid == 0) {
@@ -197,7 +188,19 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     }
     mbar_fence_init();
   }
-  if (c_end == XA_NCHUNK) {
+  if (warp == 0) {
+    // Compact list of the streams still decoding.  `done` was written by the previous step's search kernel, which
+    // completed before this step's first kernel started, so it may be read ahead of the dependency wait.
+    int base_n = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const bool alive = (b0 + lane < B) && !s.done[b0 + lane];
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (alive) live[base_n + __popc(m & ((1u << lane) - 1u))] = b0 + lane;
+      base_n += __popc(m);
+    }
+    if (lane == 0) n_live_sh = base_n;
+  }
+  {
     // the last chunk holds 92 keys: rows 92..127 of every ring buffer must be finite (their weights are exactly 0,
     // but 0 x NaN would poison the P V product).  Later full chunks leave finite K/V values there.
     constexpr int TAIL16 = (XA_CHUNK - XA_TAIL_KEYS) * 8;   // 16-byte pieces per buffer
@@ -208,44 +211,44 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     fence_proxy_async();
   }
   __syncthreads();
+  // Persistent CTA: work items (live stream, head, key range) it, it + grid, ...  The producer warp runs ahead into
+  // the next item's K chunks while the consumers are still reducing / writing out the current one.
+  const int total_items = n_live_sh * H * nsplit;
 
   if (warp == 4) {
     // ------------------------------------------------------------------ producer warp
-    // The encoder K/V of the slot were written long before this decode step: the first K chunks are requested
-    // before the dependency wait, i.e. while the q projection that precedes this kernel is still running.
+    // Encoder K/V, slot ids and done flags all predate this decode step: nothing here needs the dependency wait.
     if (elect_one()) {
-      const long head_off = (long)s.slot[b] * slot_stride + (long)h * S_ENC * 64;
       int stage = 0;
       uint32_t phase = 0;
-      bool checked = false;
-      for (int pass = 0; pass < 2; ++pass) {
-        const __half* src = (pass == 0 ? kc : vc) + head_off;
-        for (int c = c_begin; c < c_end; ++c) {
-          const int nkeys = min(XA_CHUNK, S_ENC - c * XA_CHUNK);
-          if (!checked && (pass == 1 || c - c_begin == XA_STAGES)) {
-            // ring is full for the first time: from here on the consumers must be alive
-            checked = true;
-            pdl_wait();
-            if (s.done[b]) {   // stream already finished: drain the requested chunks, then leave
-              const int issued = pass == 1 ? nchunks : XA_STAGES;
-              for (int i = 0; i < issued; ++i) mbar_wait(&full[i], 0);
-              return;
-            }
+      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        const int sp = it % nsplit, h = (it / nsplit) % H, b = live[it / (nsplit * H)];
+        const int c_begin = sp * cps, c_end = min(XA_NCHUNK, c_begin + cps);
+        const long head_off = (long)s.slot[b] * slot_stride + (long)h * S_ENC * 64;
+        for (int pass = 0; pass < 2; ++pass) {
+          const __half* src = (pass == 0 ? kc : vc) + head_off;
+          for (int c = c_begin; c < c_end; ++c) {
+            const int nkeys = min(XA_CHUNK, S_ENC - c * XA_CHUNK);
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], nkeys * 128);
+            bulk_load_1d(stage_buf + stage * XA_STAGE_BYTES, src + (long)c * XA_CHUNK * 64, nkeys * 128, &full[stage]);
+            if (++stage == XA_STAGES) { stage = 0; phase ^= 1; }
           }
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], nkeys * 128);
-          bulk_load_1d(stage_buf + stage * XA_STAGE_BYTES, src + (long)c * XA_CHUNK * 64, nkeys * 128, &full[stage]);
-          if (++stage == XA_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     return;
   }
   // -------------------------------------------------------------------- consumer warps (128 threads)
-  pdl_wait();
-  if (s.done[b]) return;
-  const int row0 = b * rows_per_stream;
+  pdl_wait();   // q comes from the projection GEMM right before this kernel
   const int g = lane >> 2, tq = lane & 3;    // mma fragment coordinates: group (row / n index), thread-in-group
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+  const int sp = it % nsplit, h = (it / nsplit) % H, b = live[it / (nsplit * H)];
+  const int c_begin = sp * cps, c_end = min(XA_NCHUNK, c_begin + cps);
+  const int nchunks = c_end - c_begin;
+  const int row0 = b * rows_per_stream;
   // q rows of this (stream, head): bias + split-K partial sums in range order, reduced cooperatively (coalesced,
   // 4 ranges in flight) into shared memory as [8][64] fp32 (rows >= rows_per_stream are zero), pre-scaled by 1/8.
   for (int idx = tid; idx < 8 * 64; idx += 128) {
@@ -274,8 +277,6 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     }
   consumers_sync();   // ored is reused at the end
 
-  int stage = 0;
-  uint32_t phase = 0;
   // ---- pass 1: scores.  Warp w owns keys [32w, 32w+32) of every chunk: 2 m-tiles x 4 k-steps.
   const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8;   // ldmatrix: row this lane addresses inside a 16-row tile
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -422,7 +423,8 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
         out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(ov / l);
       }
     }
-    return;
+    consumers_sync();   // ored / red are reused by the next item
+    continue;
   }
   float* pbase = part + ((long)b * H + h) * nsplit * MAX_ROWS_PER_STREAM * 66;
   float* dst = pbase + (long)sp * MAX_ROWS_PER_STREAM * 66;
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   consumers_sync();
   if (tid == 0) red[0] = (atomicAdd(&counters[b * H + h], 1) == nsplit - 1) ? 1.f : 0.f;
   consumers_sync();
-  if (red[0] == 0.f) return;
+  if (red[0] == 0.f) continue;
   __threadfence();
   if (tid == 0) counters[b * H + h] = 0;   // ready for the next launch
   for (int idx = tid; idx < NQ * 64; idx += 128) {
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
       out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(ov / L);
     }
   }
+  }   // item loop
 }
 
 static int xa_template_nq(int rows_per_stream) {
@@ -511,10 +514,14 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
                          int nsplit) {
   const int cps = (XA_NCHUNK + nsplit - 1) / nsplit;
   const int smem = xa_smem_bytes(cps, NQ);
-  dim3 grid(nsplit, H, B);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int occ = std::max(1, std::min(12, (227 * 1024) / (smem + 1024)));
+  WL_CHECK(B <= MAX_STREAMS_CAP, WL_ERR_ARG, "cross attention: %d streams exceed the compiled cap %d", B, MAX_STREAMS_CAP);
+  dim3 grid((unsigned)std::min<long>((long)B * H * nsplit, (long)occ * sms));
   const int stg = xa_stages();
   auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
-  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, rows_per_stream, H, d, nsplit, cps);
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, B, rows_per_stream, H, d, nsplit, cps);
   note_launch(1);
 }
 

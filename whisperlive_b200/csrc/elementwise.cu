@@ -268,6 +268,10 @@ __global__ void decoder_embed_kernel(DecodeState s, const __half* __restrict__ e
 }
 
 void decoder_embed(cudaStream_t st, const DecodeState& s, const __half* emb, const __half* pos_emb, float* x, int R, int d) {
+  // First kernel of a decode step, deliberately NOT a programmatic dependent: it starts only after everything before
+  // the step (decode_init, the previous step's search kernels) has completed, so the kernels of this step may read
+  // that per-step state (done flags, slots, positions) ahead of their own dependency wait.
+  PdlScope no_pdl(false);
   launch_kernel(decoder_embed_kernel, dim3(R), dim3(128), 0, st, s, emb, pos_emb, x, d);
   note_launch(1);
 }
