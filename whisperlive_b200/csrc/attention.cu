@@ -4,6 +4,8 @@
 //       streamed HBM -> smem by a producer warp with cp.async.bulk + mbarrier ring, consumed by 4 warps.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "kernels.cuh"
 
@@ -169,15 +171,18 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int nk_cap = cps * XA_CHUNK;
   const int ph_ld = nk_cap + 8;                                         // halves; +8 -> rows 16 B apart mod 128 B (conflict-free B fragments)
   uint8_t* stage_buf = base;                                            // XA_STAGES x 16 KB
-  float* S = reinterpret_cast<float*>(base + XA_STAGES * XA_STAGE_BYTES);  // [cps*128][SW] scores, then exp()
-  __half* Ph = reinterpret_cast<__half*>(S + (long)nk_cap * SW);        // [NQ][ph_ld] weights for the P V MMA
+  // S [cps*128][SW] holds the scores, then exp(); the same bytes serve as q staging [8][64] before the first sweep and
+  // as the cross-warp output reduction [4][8][64] after the second one (S is dead by then).
+  float* S = reinterpret_cast<float*>(base + XA_STAGES * XA_STAGE_BYTES);
+  float* ored = S;
+  const int s_floats = max(nk_cap * SW, 4 * 8 * 64);
+  __half* Ph = reinterpret_cast<__half*>(S + s_floats);                 // [NQ][ph_ld] weights for the P V MMA
   float* red = reinterpret_cast<float*>(Ph + (long)NQ * ph_ld);         // [2][4][8]
-  float* ored = red + 64;                                               // [4][8][64] output reduction; first q staging [8][64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ored + 4 * 8 * 64);
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 64);
   uint64_t* empty = full + XA_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  __shared__ int live[MAX_STREAMS_CAP];
+  __shared__ uint8_t live[MAX_STREAMS_CAP];
   __shared__ int n_live_sh;
   pdl_trigger();
 
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     for (int b0 = 0; b0 < B; b0 += 32) {
       const bool alive = (b0 + lane < B) && !s.done[b0 + lane];
       const unsigned m = __ballot_sync(0xffffffffu, alive);
-      if (alive) live[base_n + __popc(m & ((1u << lane) - 1u))] = b0 + lane;
+      if (alive) live[base_n + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(b0 + lane);
       base_n += __popc(m);
     }
     if (lane == 0) n_live_sh = base_n;
@@ -482,7 +487,29 @@ static int xa_stages() {
 static int xa_smem_bytes(int cps, int NQ) {
   const int sw = NQ <= 2 ? 2 : NQ <= 4 ? 4 : 8;
   const int nk = cps * XA_CHUNK;
-  return 128 + xa_stages() * XA_STAGE_BYTES + nk * sw * 4 + NQ * (nk + 8) * 2 + (64 + 4 * 8 * 64) * 4 + 2 * xa_stages() * 8 + 64;
+  return 128 + xa_stages() * XA_STAGE_BYTES + std::max(nk * sw, 4 * 8 * 64) * 4 + NQ * (nk + 8) * 2 + 64 * 4 + 2 * xa_stages() * 8 + 64;
+}
+
+template <int NQ>
+static const void* xa_kernel_ptr() {
+  const int stg = xa_stages();
+  return stg == 2 ? (const void*)cross_attn_kernel<NQ, 2> : stg == 4 ? (const void*)cross_attn_kernel<NQ, 4> : (const void*)cross_attn_kernel<NQ, 3>;
+}
+// resident CTAs per SM for this key-range length, asked from the runtime (cached): the grid of the persistent
+// kernel is exactly occupancy x SMs
+static int xa_occupancy(int NQ, int cps) {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const int key = NQ * 64 + cps;
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const void* k = NQ == 1 ? xa_kernel_ptr<1>() : NQ == 2 ? xa_kernel_ptr<2>() : NQ == 4 ? xa_kernel_ptr<4>() : NQ == 5 ? xa_kernel_ptr<5>() : xa_kernel_ptr<8>();
+  int occ = 0;
+  WL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 160, (size_t)xa_smem_bytes(cps, NQ)));
+  occ = std::max(1, occ);
+  cache[key] = occ;
+  return occ;
 }
 
 // Choose how many CTAs share one (stream, head): the grid should fill whole waves of resident CTAs
@@ -499,7 +526,7 @@ int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream) {
     const int real = (XA_NCHUNK + cps - 1) / cps;
     if (real != ns) continue;
     if (forced == ns) return ns;
-    const int occ = std::max(1, std::min(12, (227 * 1024) / (xa_smem_bytes(cps, NQ) + 1024)));
+    const int occ = xa_occupancy(NQ, cps);
     const long slots = (long)occ * num_sms, items = (long)B * H * ns;
     const long waves = (items + slots - 1) / slots;
     const double cost = (double)waves * (cps + 3.0);
@@ -516,7 +543,7 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   const int smem = xa_smem_bytes(cps, NQ);
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int occ = std::max(1, std::min(12, (227 * 1024) / (smem + 1024)));
+  const int occ = xa_occupancy(NQ, cps);
   WL_CHECK(B <= MAX_STREAMS_CAP, WL_ERR_ARG, "cross attention: %d streams exceed the compiled cap %d", B, MAX_STREAMS_CAP);
   dim3 grid((unsigned)std::min<long>((long)B * H * nsplit, (long)occ * sms));
   const int stg = xa_stages();
