@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
                                                          __half* __restrict__ out, int* __restrict__ counters, int B,
-                                                         int rows_per_stream, int H, int d, int nsplit, int cps) {
+                                                         int rows_per_stream, int H, int d, int nsplit, int cps, int dbg) {
   constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
   uint8_t* base = xa_smem_raw + ((128u - (smem_u32(xa_smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS/STS)
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   for (int idx = tid; idx < 8 * 64; idx += 128) {
     const int j = idx >> 6, dd = idx & 63;
     float a = 0.f;
-    if (j < rows_per_stream) {
+    if (j < rows_per_stream && !(dbg & 2)) {
       a = q.bias ? __ldg(q.bias + h * 64 + dd) : 0.f;
       const float* qp = q.ptr + (long)(row0 + j) * d + h * 64 + dd;
 #pragma unroll 4
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     for (int mt = 0; mt < 2; ++mt) {
       sc[mt][0] = sc[mt][1] = sc[mt][2] = sc[mt][3] = 0.f;
       const int key_l = warp * 32 + mt * 16 + ld_row;
+      if (dbg & 1) continue;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4];
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   float mx[NQ], sm[NQ];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) mx[j] = -INFINITY;
-  for (int k = tid; k < nk_pad; k += 128) {
+  const int nk_sm = (dbg & 4) ? 0 : nk_pad;
+  for (int k = tid; k < nk_sm; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) mx[j] = fmaxf(mx[j], S[(long)k * SW + j]);
   }
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   float sm32[NQ];   // exact fp32 sums: only the alignment probabilities use them
 #pragma unroll
   for (int j = 0; j < NQ; ++j) sm32[j] = 0.f;
-  for (int k = tid; k < nk_pad; k += 128) {
+  for (int k = tid; k < nk_sm; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
       const float e32 = __expf(S[(long)k * SW + j] - mx[j]);
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
         b1 = *reinterpret_cast<const uint32_t*>(pp + 8);
       }
       const int key_l = kbase + ldt_row;
+      if (dbg & 1) continue;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         uint32_t a[4];
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     ob[64 + 8] = o[mt][3];
   }
   consumers_sync();
+  if (dbg & 8) { consumers_sync(); continue; }
   if (nsplit == 1) {   // the whole key range was here: normalise and store the attention output directly
     for (int idx = tid; idx < NQ * 64; idx += 128) {
       const int j = idx >> 6, dd = idx & 63;
@@ -475,6 +479,12 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 
 static int xa_template_nq(int rows_per_stream) {
   return rows_per_stream == 1 ? 1 : rows_per_stream == 2 ? 2 : rows_per_stream <= 4 ? 4 : rows_per_stream == 5 ? 5 : 8;
+}
+// WLB200_XA_DBG (profiling only, results become garbage): 1 skip the MMA work, 2 skip the q reduction, 4 skip the
+// softmax pass, 8 skip the write-out / merge -- isolates how much of the kernel time is pure K/V streaming
+static int xa_dbg() {
+  static const int v = [] { const char* e = getenv("WLB200_XA_DBG"); return e ? atoi(e) : 0; }();
+  return v;
 }
 static int xa_stages() {
   static const int st = [] {
@@ -548,7 +558,7 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   dim3 grid((unsigned)std::min<long>((long)B * H * nsplit, (long)occ * sms));
   const int stg = xa_stages();
   auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
-  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, B, rows_per_stream, H, d, nsplit, cps);
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
   note_launch(1);
 }
 

@@ -17,6 +17,7 @@ using namespace wl;
 namespace wl {
 void gemm_prime();
 void attention_prime();
+void search_prime();
 void flash_attn_prime();
 void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt, __half* out, int nb, int H, int d);
 long other_launch_count();
@@ -173,6 +174,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     WL_CUDA(cudaEventCreate(&c->ev1));
     gemm_prime();
     attention_prime();
+    search_prime();
     flash_attn_prime();
     c->enc.resize(c->Le);
     c->dec.resize(c->Ld);

@@ -13,8 +13,8 @@ struct MaskCtx {
   int eot, no_timestamps, ts_begin, blank;
 };
 
-__device__ __forceinline__ bool tok_masked(int t, const MaskCtx& c) {
-  if (c.suppress[t >> 5] & (1u << (t & 31))) return true;
+// the rule-based part of the logits processors (everything but the user's suppress list)
+__device__ __forceinline__ bool rule_masked(int t, const MaskCtx& c) {
   if (c.first && c.suppress_blank && (t == c.blank || t == c.eot)) return true;
   if (c.use_ts) {
     if (t == c.no_timestamps) return true;
@@ -46,7 +46,11 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
   else s += s2 * __expf(m2 - m);
 }
 
-__device__ void block_lse(float& m, float& s, float* red /*[16]*/) {
+constexpr int SR_THREADS = 1024;
+constexpr int SR_WARPS = SR_THREADS / 32;
+
+// block-wide (max, sum-of-exp) merge; red holds 2 x SR_WARPS floats
+__device__ void block_lse(float& m, float& s, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -54,31 +58,54 @@ __device__ void block_lse(float& m, float& s, float* red /*[16]*/) {
   }
   const int w = threadIdx.x >> 5;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) { red[w] = m; red[8 + w] = s; }
+  if ((threadIdx.x & 31) == 0) { red[w] = m; red[SR_WARPS + w] = s; }
   __syncthreads();
-  m = red[0]; s = red[8];
-  for (int i = 1; i < 8; ++i) lse_merge(m, s, red[i], red[8 + i]);
+  m = red[0]; s = red[SR_WARPS];
+  for (int i = 1; i < SR_WARPS; ++i) lse_merge(m, s, red[i], red[SR_WARPS + i]);
+  __syncthreads();
+}
+// block-wide max / sum of two values at once
+__device__ void block_max2(float& a, float& b, float* red) {
+  a = warp_max(a); b = warp_max(b);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[SR_WARPS + w] = b; }
+  __syncthreads();
+  a = warp_max(red[threadIdx.x & 31]); b = warp_max(red[SR_WARPS + (threadIdx.x & 31)]);
+  __syncthreads();
+}
+__device__ void block_sum2(float& a, float& b, float* red) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[SR_WARPS + w] = b; }
+  __syncthreads();
+  // fixed order: every thread adds the 32 warp sums in the same sequence
+  float x = 0.f, y = 0.f;
+#pragma unroll
+  for (int i = 0; i < SR_WARPS; ++i) { x += red[i]; y += red[SR_WARPS + i]; }
+  a = x; b = y;
   __syncthreads();
 }
 
-constexpr int SR_THREADS = 256;
-
+// One 1024-thread CTA per decoder row.  The row of logits (<= 53248 floats, 207 KB for the 51866-token vocabulary)
+// is read from HBM/L2 exactly once: it is masked on the way in (suppress list + timestamp rules -> -inf) and kept in
+// shared memory; the softmax statistics, the key computation and the candidate rounds all run on the resident copy.
+// Candidates: each thread remembers the best of its own 4-token groups; a round is one block arg-max over those
+// (ties -> lower token id) after which only the winning thread looks for its next-best entry.
 __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, const float* __restrict__ logits, SearchOpts o,
                                                                  VocabIds v) {
+  extern __shared__ float4 sr_smem[];   // [n4] masked logits, later selection keys
   const int r = blockIdx.x, tid = threadIdx.x;
   const int b = r / o.rows_per_stream;
   pdl_trigger();
-  pdl_wait();
-  if (!s.active[r] || s.done[b]) return;
-  __shared__ float red[16];
-  __shared__ float lkey[MAX_CAND][SR_THREADS];   // per-thread sorted lists, thread index fastest (no bank conflicts)
-  __shared__ int ltok[MAX_CAND][SR_THREADS];
-  __shared__ float wkey[8];
-  __shared__ int wtok[8], wtid[8];
+  if (!s.active[r] || s.done[b]) return;   // per-step state, complete before this step started
+  __shared__ float red[2 * SR_WARPS];
+  __shared__ float wkey[SR_WARPS];
+  __shared__ int wtok[SR_WARPS], wtid[SR_WARPS];
   __shared__ int win_tid;
 
   const float* lg = logits + (long)r * v.vocab_ld;
   const int fed = s.fed[b], P = s.prompt_len[b];
+  pdl_wait();   // logits come from the vocabulary GEMM right before this kernel
   if (fed == s.sot_index[b] && r == b * o.rows_per_stream) {
     float m = -INFINITY, sm = 0.f;
     for (int t = tid; t < v.vocab; t += SR_THREADS) lse_merge(m, sm, lg[t], 1.f);
@@ -113,27 +140,41 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   c.has_ts = lts >= 0;
   c.ts_cutoff = (c.last_is_ts && !c.penult_is_ts) ? lts : lts + 1;
 
-  // pass 1: softmax statistics of the text part and the timestamp part after masks a-d
-  float mt = -INFINITY, st = 0.f, mz = -INFINITY, sz = 0.f;
+  // load + mask (processors a-d) -> shared memory; thread-local maxima of the text and the timestamp part
   const float4* lg4 = reinterpret_cast<const float4*>(lg);
   const int n4 = v.vocab_ld >> 2;
-  auto stat = [&](int t, float x) {
-    if (t >= v.vocab || tok_masked(t, c)) return;
-    if (t < v.ts_begin) lse_merge(mt, st, x, 1.f);
-    else lse_merge(mz, sz, x, 1.f);
-  };
-  for (int i0 = tid; i0 < n4; i0 += 4 * SR_THREADS) {
-    float4 q[4];
+  float mt = -INFINITY, mz = -INFINITY;
+  for (int i4 = tid; i4 < n4; i4 += SR_THREADS) {
+    const int t = 4 * i4;
+    const float4 q = lg4[i4];
+    const unsigned bits = t < v.vocab ? (c.suppress[t >> 5] >> (t & 31)) : 0xFu;   // 4 | 32: the 4 tokens share a word
+    float x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = (i0 + u * SR_THREADS < n4) ? lg4[i0 + u * SR_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < 4; ++e) {
+      const bool masked = t + e >= v.vocab || ((bits >> e) & 1u) || rule_masked(t + e, c);
+      x[e] = masked ? -INFINITY : x[e];
+      if (t + e < v.ts_begin) mt = fmaxf(mt, x[e]);
+      else mz = fmaxf(mz, x[e]);
+    }
+    sr_smem[i4] = make_float4(x[0], x[1], x[2], x[3]);
+  }
+  block_max2(mt, mz, red);
+  // softmax statistics of the two parts (exp of -inf is 0: masked entries drop out)
+  float st = 0.f, sz = 0.f;
+  {
+    const float mt0 = mt == -INFINITY ? 0.f : mt, mz0 = mz == -INFINITY ? 0.f : mz;
+    for (int i4 = tid; i4 < n4; i4 += SR_THREADS) {
+      const int t = 4 * i4;
+      const float4 q = sr_smem[i4];
+      const float x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = 4 * (i0 + u * SR_THREADS);
-      if (t < v.vocab) { stat(t, q[u].x); stat(t + 1, q[u].y); stat(t + 2, q[u].z); stat(t + 3, q[u].w); }
+      for (int e = 0; e < 4; ++e) {
+        if (t + e < v.ts_begin) st += __expf(x[e] - mt0);
+        else sz += __expf(x[e] - mz0);
+      }
     }
   }
-  block_lse(mt, st, red);
-  block_lse(mz, sz, red);
+  block_sum2(st, sz, red);
   const float lse_text = st > 0.f ? mt + logf(st) : -INFINITY;
   const float lse_ts = sz > 0.f ? mz + logf(sz) : -INFINITY;
   const bool text_off = c.use_ts && !c.first && lse_ts > mt;  // rule e: mass on timestamps beats the best text token
@@ -145,44 +186,36 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
     lse = hi + log1pf(expf(lo - hi));
   }
 
-  // pass 2: thread-local sorted top-NC, then NC rounds of block arg-max over the list heads
+  // selection keys in place: log-prob (beam / greedy) or log-prob / T + Gumbel noise (sampling); rule e drops text
   const int NC = o.beam > 1 ? 2 * o.beam : 1;
-  int cnt = 0;
   uint32_t gkey = 0;
   if (o.sampling) gkey = hash_u32((o.seed * 0x9E3779B1u) ^ hash_u32((uint32_t)((b * 64 + (r - b * o.rows_per_stream)) * 65537 + s.step[b])));
-  auto consider = [&](int t, float x) {
-    if (t >= v.vocab || tok_masked(t, c)) return;
-    if (text_off && t < v.ts_begin) return;
-    const float lp = x - lse;
-    float key = lp;
-    if (o.sampling) {
-      const double u = ((double)hash_u32((uint32_t)t ^ gkey) + 0.5) / 4294967296.0;
-      key = __fdiv_rn(lp, o.temperature) + (float)(-log(-log(u)));
-    }
-    if (cnt == NC && !(key > lkey[NC - 1][tid])) return;
-    int i = cnt < NC ? cnt : NC - 1;
-    while (i > 0 && key > lkey[i - 1][tid]) {
-      lkey[i][tid] = lkey[i - 1][tid]; ltok[i][tid] = ltok[i - 1][tid];
-      --i;
-    }
-    lkey[i][tid] = key; ltok[i][tid] = t;
-    if (cnt < NC) ++cnt;
-  };
-  for (int i0 = tid; i0 < n4; i0 += 4 * SR_THREADS) {
-    float4 q[4];
+  float bk = -INFINITY;        // this thread's best remaining entry
+  int bt = 0x7fffffff;
+  for (int i4 = tid; i4 < n4; i4 += SR_THREADS) {
+    const int t = 4 * i4;
+    const float4 q = sr_smem[i4];
+    float x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = (i0 + u * SR_THREADS < n4) ? lg4[i0 + u * SR_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = 4 * (i0 + u * SR_THREADS);
-      if (t < v.vocab) { consider(t, q[u].x); consider(t + 1, q[u].y); consider(t + 2, q[u].z); consider(t + 3, q[u].w); }
+    for (int e = 0; e < 4; ++e) {
+      float key = -INFINITY;
+      if (x[e] > -INFINITY && !(text_off && t + e < v.ts_begin)) {
+        const float lp = x[e] - lse;
+        key = lp;
+        if (o.sampling) {
+          const double u = ((double)hash_u32((uint32_t)(t + e) ^ gkey) + 0.5) / 4294967296.0;
+          key = __fdiv_rn(lp, o.temperature) + (float)(-log(-log(u)));
+        }
+        if (key > bk) { bk = key; bt = t + e; }   // ascending token order: strict > keeps the lowest id among equals
+      }
+      x[e] = key;
     }
+    sr_smem[i4] = make_float4(x[0], x[1], x[2], x[3]);
   }
-  int hd = 0;
+  const float* keys = reinterpret_cast<const float*>(sr_smem);
   for (int round = 0; round < NC; ++round) {
-    float k = hd < cnt ? lkey[hd][tid] : -INFINITY;
-    int t = hd < cnt ? ltok[hd][tid] : 0x7fffffff;
-    int who = tid;
+    float k = bk;
+    int t = bt, who = tid;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const float k2 = __shfl_xor_sync(0xffffffffu, k, off);
@@ -191,26 +224,48 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
     }
     if ((tid & 31) == 0) { wkey[tid >> 5] = k; wtok[tid >> 5] = t; wtid[tid >> 5] = who; }
     __syncthreads();
-    if (tid == 0) {
-      float bk = wkey[0]; int bt = wtok[0], bw = wtid[0];
-      for (int w = 1; w < 8; ++w)
-        if (wkey[w] > bk || (wkey[w] == bk && wtok[w] < bt)) { bk = wkey[w]; bt = wtok[w]; bw = wtid[w]; }
-      win_tid = bt == 0x7fffffff ? -1 : bw;
-      if (win_tid < 0) { s.cand_val[(long)r * MAX_CAND + round] = -INFINITY; s.cand_tok[(long)r * MAX_CAND + round] = -1; }
+    if (tid < 32) {
+      k = wkey[tid]; t = wtok[tid]; who = wtid[tid];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float k2 = __shfl_xor_sync(0xffffffffu, k, off);
+        const int t2 = __shfl_xor_sync(0xffffffffu, t, off), w2 = __shfl_xor_sync(0xffffffffu, who, off);
+        if (k2 > k || (k2 == k && t2 < t)) { k = k2; t = t2; who = w2; }
+      }
+      if (tid == 0) {
+        const bool none = t == 0x7fffffff;
+        win_tid = none ? -1 : who;
+        s.cand_val[(long)r * MAX_CAND + round] = none ? -INFINITY : lg[t] - lse;
+        s.cand_tok[(long)r * MAX_CAND + round] = none ? -1 : t;
+      }
     }
     __syncthreads();
     if (tid == win_tid) {
-      s.cand_val[(long)r * MAX_CAND + round] = lg[ltok[hd][tid]] - lse;
-      s.cand_tok[(long)r * MAX_CAND + round] = ltok[hd][tid];
-      ++hd;
+      // next-best entry of this thread: strictly after (bk, bt) in (key descending, token ascending) order
+      const float pk = bk;
+      const int pt = bt;
+      bk = -INFINITY; bt = 0x7fffffff;
+      for (int i4 = tid; i4 < n4; i4 += SR_THREADS) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int tt = 4 * i4 + e;
+          const float key = keys[tt];
+          if (key > -INFINITY && (key < pk || (key == pk && tt > pt)) && key > bk) { bk = key; bt = tt; }
+        }
+      }
     }
-    __syncthreads();
   }
 }
 
 void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, const SearchOpts& o, const VocabIds& v, int R) {
-  launch_kernel(search_rows_kernel, dim3(R), dim3(SR_THREADS), 0, st, s, logits, o, v);
+  const size_t smem = (size_t)(v.vocab_ld >> 2) * sizeof(float4);
+  WL_CHECK(v.vocab_ld % 4 == 0 && smem <= 216 * 1024, WL_ERR_ARG, "search_rows: vocabulary row of %d floats does not fit in shared memory", v.vocab_ld);
+  launch_kernel(search_rows_kernel, dim3(R), dim3(SR_THREADS), smem, st, s, logits, o, v);
   note_launch(1);
+}
+
+void search_prime() {
+  WL_CUDA(cudaFuncSetAttribute(search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
 }
 
 // ============================================================================ per-stream state machine
