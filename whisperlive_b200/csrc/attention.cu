@@ -249,23 +249,35 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int g = lane >> 2, tq = lane & 3;    // mma fragment coordinates: group (row / n index), thread-in-group
   int stage = 0;
   uint32_t phase = 0;
+  constexpr int MAX_QSPLIT = 8;                 // gemm_split_plan never exceeds 8 K ranges
+  float qraw[4][1 + MAX_QSPLIT];                // this thread's 4 entries of q[8][64]: bias + raw partial sums
+  auto q_fetch = [&](int item) {
+    const int h2 = (item / nsplit) % H, b2 = live[item / (nsplit * H)];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 128, j = idx >> 6, dd = idx & 63;
+      const bool ok = j < rows_per_stream && !(dbg & 2);
+      qraw[e][0] = (ok && q.bias) ? __ldg(q.bias + h2 * 64 + dd) : 0.f;
+      const float* qp = q.ptr + (long)(b2 * rows_per_stream + (ok ? j : 0)) * d + h2 * 64 + dd;
+#pragma unroll
+      for (int sq = 0; sq < MAX_QSPLIT; ++sq) qraw[e][1 + sq] = (ok && sq < q.nsplit) ? __ldcg(qp + (long)sq * q.stride) : 0.f;
+    }
+  };
   for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
   const int sp = it % nsplit, h = (it / nsplit) % H, b = live[it / (nsplit * H)];
   const int c_begin = sp * cps, c_end = min(XA_NCHUNK, c_begin + cps);
   const int nchunks = c_end - c_begin;
   const int row0 = b * rows_per_stream;
-  // q rows of this (stream, head): bias + split-K partial sums in range order, reduced cooperatively (coalesced,
-  // 4 ranges in flight) into shared memory as [8][64] fp32 (rows >= rows_per_stream are zero), pre-scaled by 1/8.
-  for (int idx = tid; idx < 8 * 64; idx += 128) {
-    const int j = idx >> 6, dd = idx & 63;
-    float a = 0.f;
-    if (j < rows_per_stream && !(dbg & 2)) {
-      a = q.bias ? __ldg(q.bias + h * 64 + dd) : 0.f;
-      const float* qp = q.ptr + (long)(row0 + j) * d + h * 64 + dd;
-#pragma unroll 4
-      for (int sq = 0; sq < q.nsplit; ++sq) a += __ldcg(qp + (long)sq * q.stride);
-    }
-    ored[idx] = a * 0.125f;
+  // q rows of this (stream, head) as [8][64] fp32 in shared memory (rows >= rows_per_stream are zero), pre-scaled by
+  // 1/8.  The raw split-K partial sums of the NEXT item are requested in the middle of the current one (see below)
+  // so that their latency never stalls the K/V stream; only the very first item of a CTA loads them here.
+  if (it == (int)blockIdx.x) q_fetch(it);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a = qraw[e][0];   // bias
+#pragma unroll
+    for (int sq = 0; sq < MAX_QSPLIT; ++sq) a += qraw[e][1 + sq];   // K ranges in index order
+    ored[tid + e * 128] = a * 0.125f;
   }
   consumers_sync();
   // B fragments of q^T (k = dim, n = row): lane holds q[g][ks*16 + 2*tq + {0,1}] and [.. + 8], as hi + lo halves
@@ -317,6 +329,8 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
       }
     }
   }
+  // request the next item's q partial sums now: they arrive while the softmax pass and the V sweep run
+  if (it + (int)gridDim.x < total_items) q_fetch(it + gridDim.x);
   consumers_sync();
   // ---- softmax statistics over this CTA's key range
   const int nk_pad = nchunks * XA_CHUNK;
@@ -348,9 +362,11 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
       const float e32 = __expf(S[(long)k * SW + j] - mx[j]);
       const __half eh = __float2half_rn(e32);
       Ph[(long)j * ph_ld + k] = eh;
-      S[(long)k * SW + j] = e32;
       sm[j] += __half2float(eh);
-      sm32[j] += e32;
+      if (probs != nullptr) {
+        S[(long)k * SW + j] = e32;
+        sm32[j] += e32;
+      }
     }
   }
 #pragma unroll
@@ -449,32 +465,29 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     dst[tid * 66 + 0] = mx[tid];
     dst[tid * 66 + 1] = sm[tid];
   }
-  // The CTA that finishes a (stream, head) last merges its nsplit partial softmaxes (in key-range order, so the
-  // result does not depend on which CTA that is) -- no separate combine launch.
-  __threadfence();
-  consumers_sync();
-  if (tid == 0) red[0] = (atomicAdd(&counters[b * H + h], 1) == nsplit - 1) ? 1.f : 0.f;
-  consumers_sync();
-  if (red[0] == 0.f) continue;
-  __threadfence();
-  if (tid == 0) counters[b * H + h] = 0;   // ready for the next launch
-  for (int idx = tid; idx < NQ * 64; idx += 128) {
-    const int j = idx >> 6, dd = idx & 63;
-    if (j < rows_per_stream) {
-      const float* pj = pbase + j * 66;
-      float M = -INFINITY;
-      for (int q2 = 0; q2 < nsplit; ++q2) M = fmaxf(M, __ldcg(pj + (long)q2 * MAX_ROWS_PER_STREAM * 66));
-      float L = 0.f, ov = 0.f;
-      for (int q2 = 0; q2 < nsplit; ++q2) {
-        const float* ps = pj + (long)q2 * MAX_ROWS_PER_STREAM * 66;
-        const float w = __expf(__ldcg(ps) - M);
-        L += __ldcg(ps + 1) * w;
-        ov += __ldcg(ps + 2 + dd) * w;
-      }
-      out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(ov / L);
-    }
-  }
+  consumers_sync();   // ored is rewritten by the next item
   }   // item loop
+}
+
+// merge the nsplit partial softmaxes of every (row, head), in key-range order
+__global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict__ part, __half* __restrict__ out,
+                                          int rows_per_stream, int H, int d, int nsplit) {
+  const int r = blockIdx.y, h = blockIdx.x, dd = threadIdx.x;
+  const int b = r / rows_per_stream, j = r % rows_per_stream;
+  pdl_trigger();
+  if (s.done[b]) return;
+  pdl_wait();
+  const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
+  float M = -INFINITY;
+  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(p + (long)sp * MAX_ROWS_PER_STREAM * 66));
+  float L = 0.f, o = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
+    const float w = __expf(__ldcg(ps) - M);
+    L += __ldcg(ps + 1) * w;
+    o += __ldcg(ps + 2 + dd) * w;
+  }
+  out[(long)r * d + h * 64 + dd] = __float2half_rn(o / L);
 }
 
 static int xa_template_nq(int rows_per_stream) {
@@ -580,11 +593,16 @@ void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc&
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit) {
   WL_CHECK(rows_per_stream >= 1 && rows_per_stream <= MAX_ROWS_PER_STREAM, WL_ERR_ARG, "rows per stream %d", rows_per_stream);
+  WL_CHECK(q.nsplit >= 1 && q.nsplit <= 8, WL_ERR_ARG, "cross attention: q arrives in %d K ranges (1..8 supported)", q.nsplit);
   if (rows_per_stream == 1) launch_cross<1>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream == 2) launch_cross<2>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream <= 4) launch_cross<4>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  if (nsplit > 1) {
+    launch_kernel(cross_attn_combine_kernel, dim3(H, B * rows_per_stream), dim3(64), 0, st, s, ws.part, out, rows_per_stream, H, d, nsplit);
+    note_launch(1);
+  }
 }
 
 }  // namespace wl
