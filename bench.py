@@ -295,7 +295,7 @@ def main():
     d2h = sum((len(w) // 160 + 1) * dims.n_mels * 4 for w in my_waves) + n_local * args.beam * 448 * 4
 
     # ---- roofline of the dominant kernel (cross-attention K/V streaming), measured live
-    roof = dominant_kernel_roofline(eng, dims, n_local, args.beam)
+    roof = dominant_kernel_roofline(eng, dims, n_local, args.beam, feats_cache)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -328,30 +328,62 @@ def main():
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(eng, dims, n_streams, beam):
-    """Cross-attention (K11) streams 2*1500*d fp16 per stream per decoder layer per step: time the decode
-    loop with events and attribute bytes = algorithmic bytes of the whole step."""
+def dominant_kernel_roofline(eng, dims, n_streams, beam, feats_cache):
+    """Roofline of the dominant kernel, decoder cross-attention (K11, cross_attn_kernel): one launch streams the
+    encoder K and V of every live stream for one layer, 2 * 1500 * d_model fp16 values per stream (DESIGN.md
+    section 4) -- HBM-bound.  Its launch duration is measured live: a short graph-less generate pass over the
+    bench's own resident encoder outputs with CUDA events around every launch on the library stream
+    (wl_profile_cross_attn).  `step` keeps the whole decode loop (weights + cross-KV + self-KV per token) for context."""
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    which = "measured burst copy bandwidth (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     d, L, V = dims.d_model, dims.dec_layers, dims.vocab
-    w_step = (14 * d * d * L + V * d) * 2
-    kv_cross = n_streams * L * 2 * 1500 * d * 2
+    # whole decode loop of the last timed generate call
     steps = eng.last_steps if hasattr(eng, "last_steps") else None
     ms = eng.last_device_ms(2)
-    if not steps or ms <= 0:
-        return {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": which}
-    avg_t = 0.5 * steps  # self-attention cache grows linearly; mean length over the loop
-    kv_self = n_streams * beam * L * 2 * avg_t * d * 2
-    bytes_step = w_step + kv_cross + kv_self
-    achieved = bytes_step * steps / (ms / 1000.0) / 1e9
-    return {"bound": "hbm", "kernel": "decoder step (weights + cross-KV + self-KV streaming; K9-K12)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "algorithmic_bytes_per_step": int(bytes_step), "steps": int(steps), "peak_source": which}
+    step_info = None
+    if steps and ms > 0:
+        w_step = (14 * d * d * L + V * d) * 2
+        kv_cross = n_streams * L * 2 * 1500 * d * 2
+        kv_self = n_streams * beam * L * 2 * (0.5 * steps) * d * 2   # cache grows linearly: mean length over the loop
+        bytes_step = w_step + kv_cross + kv_self
+        ach = bytes_step * steps / (ms / 1000.0) / 1e9
+        step_info = {"what": "decode loop: weights + cross-KV + self-KV per token (K9-K12)", "achieved": ach, "frac": ach / peak,
+                     "algorithmic_bytes_per_step": int(bytes_step), "steps": int(steps), "ms_per_token_step": ms / steps}
+    # the kernel itself
+    graph0 = eng.use_cuda_graph
+    kw = dict(feats_cache["gen_kw"])
+    kw["max_length"] = 2 * 12
+    kw["max_length_per_stream"] = [2 * 12] * n_streams          # 12 decode steps: every stream stays live
+    try:
+        eng.use_cuda_graph = False
+        eng.profile_cross_attn(True)
+        eng.generate(feats_cache["enc"], feats_cache["prompts"], **kw)
+        avg_ms, n_launch = eng.last_device_ms(3), int(eng.last_device_ms(4))
+    finally:
+        eng.profile_cross_attn(False)
+        eng.use_cuda_graph = graph0
+    alg = n_streams * 2 * 1500 * d * 2          # bytes one launch has to read: K and V of every stream, fp16
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel at this configuration
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["cross_attn_kernel"]
+        if int(t.get("streams", -1)) == n_streams and t.get("model") == dims.name:
+            traffic = float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    if avg_ms <= 0:
+        return {"bound": "hbm", "kernel": "cross_attn_kernel (K11)", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": traffic, "peak_source": which, "step": step_info}
+    achieved = alg / (avg_ms / 1000.0) / 1e9
+    return {"bound": "hbm", "kernel": "cross_attn_kernel (K11 decoder cross-attention, one launch per decoder layer per token)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": int(alg), "avg_launch_us": 1000.0 * avg_ms, "launches_timed": n_launch,
+            "timing": "CUDA events around each launch on the library stream (includes the launch gap), graph-less pass",
+            "peak_source": which, "step": step_info}
 
 
 if __name__ == "__main__":

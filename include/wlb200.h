@@ -118,8 +118,12 @@ int wl_bench_gemm(wl_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t batch, i
                   float* ms_out); /* flags: 1 transposed store, 2 bias, 4 GELU, 8 fp32 output + fp32 residual */
 /* launches of library kernels since wl_init (gpu_launches accounting in bench.py) */
 int64_t wl_kernel_launches(wl_ctx* ctx);
-/* time (ms, CUDA events on the library stream) of the last wl_mel / wl_encode / wl_generate device work */
-float wl_last_device_ms(wl_ctx* ctx, int32_t which /*0 mel, 1 encode, 2 generate*/);
+/* time (ms, CUDA events on the library stream) of the last wl_mel / wl_encode / wl_generate device work;
+ * which = 3: average ms per cross-attention kernel launch since wl_profile_cross_attn(ctx, 1), 4: launches timed */
+float wl_last_device_ms(wl_ctx* ctx, int32_t which /*0 mel, 1 encode, 2 generate, 3/4 cross-attention profile*/);
+/* enable = 1: wl_generate calls made WITHOUT a CUDA graph bracket every cross-attention launch (K11, the dominant
+ * decode kernel) with CUDA events on the library stream -- bench.py's live roofline measurement.  Resets the sums. */
+int wl_profile_cross_attn(wl_ctx* ctx, int32_t enable);
 /* resident-input variants for bench.py `value`: inputs already uploaded by the previous call of the
  * host variant are reused (no H2D, no D2H) */
 int wl_mel_resident(wl_ctx* ctx);

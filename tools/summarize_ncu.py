@@ -2,6 +2,7 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/launches_r1.md
     python tools/summarize_ncu.py report   gpurun_out/prof_attn_r1.ncu-rep profiles/prof_attn_r1.md
+    python tools/summarize_ncu.py traffic  gpurun_out/prof_cross_r1.ncu-rep profiles/traffic_r1.json cross_attn_kernel large-v3 32
 """
 import csv
 import io
@@ -53,6 +54,34 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, kernel, model, streams):
+    """Per-launch DRAM bytes (read + write) of `kernel` from a --set full capture -> JSON read by bench.py."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals, times = [], []
+    for row in data:
+        if kernel not in row[idx["Kernel Name"]]:
+            continue
+        rb = float(row[idx["dram__bytes_read.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_read.sum"]], 1)
+        wb = float(row[idx["dram__bytes_write.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_write.sum"]], 1)
+        vals.append(rb + wb)
+        t = float(row[idx["gpu__time_duration.sum"]].replace(",", ""))
+        times.append(t * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1e-3))
+    doc = {}
+    if os.path.exists(dst):
+        doc = json.load(open(dst))
+    doc[kernel] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals), "profiled_launch_us": sum(times) / len(times),
+                   "model": model, "streams": int(streams), "source": os.path.basename(src),
+                   "how": "ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches"}
+    json.dump(doc, open(dst, "w"), indent=1)
+    print(json.dumps(doc[kernel]))
+
+
 def report(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
@@ -80,6 +109,10 @@ def report(src, dst):
             f.write("\n")
     print(open(dst).read()[:6000])
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
+    traffic(*sys.argv[2:7])
+    sys.exit(0)
 
 if __name__ == "__main__":
     {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])

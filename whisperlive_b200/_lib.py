@@ -63,6 +63,7 @@ SIGNATURES = {
     "wl_bench_gemm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p]),
     "wl_kernel_launches": (C.c_int64, [C.c_void_p]),
     "wl_last_device_ms": (C.c_float, [C.c_void_p, C.c_int32]),
+    "wl_profile_cross_attn": (C.c_int, [C.c_void_p, C.c_int32]),
     "wl_mel_resident": (C.c_int, [C.c_void_p]),
     "wl_encode_resident": (C.c_int, [C.c_void_p, C.c_int32, c_i32p]),
 }

@@ -163,7 +163,7 @@ template <int NQ, int XA_STAGES>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          long slot_stride, float* __restrict__ part, float* __restrict__ probs,
-                                                         __half* __restrict__ out, int* __restrict__ counters, int B,
+                                                         __half* __restrict__ out, int B,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps, int dbg) {
   constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
@@ -571,7 +571,9 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   dim3 grid((unsigned)std::min<long>((long)B * H * nsplit, (long)occ * sms));
   const int stg = xa_stages();
   auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
-  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, ws.counters, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
+  if (ws.ev0) WL_CUDA(cudaEventRecord(ws.ev0, st));
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
+  if (ws.ev1) WL_CUDA(cudaEventRecord(ws.ev1, st));
   note_launch(1);
 }
 

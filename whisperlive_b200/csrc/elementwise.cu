@@ -116,10 +116,11 @@ __global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict
     }
   }
   if (upd.nsplit > 0) {
-    // K ranges are added in index order (bit-reproducible); the loads of 4 ranges x 3 columns are in flight together
+    // K ranges are added in index order (bit-reproducible); gemm_split_plan makes at most 8 of them, so the loop
+    // unrolls completely and all 8 x 3 loads are in flight together (one L2 round trip)
     const float4* p4 = reinterpret_cast<const float4*>(upd.ptr + row * d);
     const long st4 = upd.stride >> 2;
-#pragma unroll 4
+#pragma unroll 8
     for (int s = 0; s < upd.nsplit; ++s) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {

@@ -47,6 +47,11 @@ struct wl_ctx {
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms[3] = {0, 0, 0};
+  // per-kernel profiling of the dominant decode kernel (bench.py roofline): events around every cross-attention launch
+  int prof_cross = 0;
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+  double prof_cross_ms = 0.0;
+  long prof_cross_n = 0;
   int num_sms = 148;
   int d, H, Le, Ld, n_mels, V, Vld, Bm, Km, Rm, NS;
   bool finalized = false;
@@ -208,7 +213,24 @@ extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_
 extern "C" int64_t wl_kernel_launches(wl_ctx* c) {
   return c ? gemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
 }
-extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) { return (c && which >= 0 && which < 3) ? c->last_ms[which] : -1.f; }
+extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) {
+  if (!c) return -1.f;
+  if (which >= 0 && which < 3) return c->last_ms[which];
+  if (which == 3) return c->prof_cross_n > 0 ? (float)(c->prof_cross_ms / (double)c->prof_cross_n) : -1.f;   // avg ms per cross-attention launch
+  if (which == 4) return (float)c->prof_cross_n;
+  return -1.f;
+}
+extern "C" int wl_profile_cross_attn(wl_ctx* c, int32_t enable) {
+  API_BEGIN(c)
+  if (enable && !c->pev0) {
+    WL_CUDA(cudaEventCreate(&c->pev0));
+    WL_CUDA(cudaEventCreate(&c->pev1));
+  }
+  c->prof_cross = enable ? 1 : 0;
+  c->prof_cross_ms = 0.0;
+  c->prof_cross_n = 0;
+  API_END(c)
+}
 
 // ------------------------------------------------------------------------------------------ weights
 extern "C" int wl_load_tensor(wl_ctx* c, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
@@ -407,7 +429,6 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
   c->xws.part = dalloc<float>(c, (size_t)c->Bm * H * 12 * MAX_ROWS_PER_STREAM * 66);
   c->xws.probs = nullptr;
-  c->xws.counters = dalloc<int>(c, (size_t)c->Bm * H);
   c->suppress_mask = dalloc<unsigned>(c, (V + 31) / 32 + 1);
   if (!c->align_heads.empty()) {
     c->align_heads_dev = dalloc<int>(c, c->align_heads.size());
@@ -691,8 +712,18 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc);
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool prof = c->prof_cross && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    if (prof) { ws.ev0 = c->pev0; ws.ev1 = c->pev1; }
     decoder_cross_attn(st, s, qc, c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz, c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz,
                        slot_sz, ws, c->datt, B, Kr, H, d, nsplit);
+    if (prof) {   // profiling pass only: serialises the host with the device
+      float ms = 0.f;
+      WL_CUDA(cudaEventSynchronize(c->pev1));
+      WL_CUDA(cudaEventElapsedTime(&ms, c->pev0, c->pev1));
+      c->prof_cross_ms += ms;
+      c->prof_cross_n += 1;
+    }
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
     pending = part_gemm(L.w_oc, d, d, c->datt, c->part2, L.b_oc);

@@ -26,8 +26,9 @@ struct GemmKParams {
   GemmEpilogue e;
   int vec_ok;  // row-major output, 16-byte aligned rows: use vector stores
   int nz;           // batch entries (or K splits in accum mode): tiles = tiles_m * tiles_n * nz
-  int accum;        // 1: grid z enumerates K ranges; partial sums are atomically added to the fp32 output
+  int accum;        // 1: grid z enumerates K ranges; range s stores its partial sum at out + s * part_stride
   int kb_per_split; // k-blocks per split (accum mode)
+  int n_fastest;    // tile order, see tile_decode()
 };
 
 constexpr int BM = 128;
@@ -147,6 +148,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   }
 }
 
+// Tile order inside one batch entry.  m fastest: CTAs running side by side share the B tile (right when B is the big
+// operand).  n fastest (p.n_fastest): they share the A tile and sweep B -- right when B is a weight matrix that stays
+// in L2 anyway and A is a large activation (FC2 of the encoder: A = 123 MB would otherwise be re-read per n tile).
+__device__ __forceinline__ void tile_decode(const GemmKParams& p, int t, int tiles_m, int tiles_n, int& tile_m, int& tile_n, int& zz) {
+  if (p.n_fastest) {
+    tile_n = t % tiles_n;
+    const int r = t / tiles_n;
+    tile_m = r % tiles_m;
+    zz = r / tiles_m;
+  } else {
+    tile_m = t % tiles_m;
+    const int r = t / tiles_m;
+    tile_n = r % tiles_n;
+    zz = r / tiles_n;
+  }
+}
+
 // Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile_m fastest, so CTAs
 // running side by side share the B (weight) tile in L2).  Two TMEM accumulator stages: the epilogue warps drain
 // tile i while the MMA warp already accumulates tile i+1.
@@ -207,7 +225,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return pos[0] == s ? row : (pos[1] == s ? j1 : (pos[2] == s ? j2 : 0));
       };
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
+        int tile_m, tile_n, zz;
+        tile_decode(p, t, tiles_m, tiles_n, tile_m, tile_n, zz);
         const int z = KIND == EPI_PART ? 0 : zz, split = KIND == EPI_PART ? zz : 0;
         const int i1 = z % p.zn1, i2 = z / p.zn1;
         const int kb0 = KIND == EPI_PART ? split * p.kb_per_split : 0;
@@ -252,7 +271,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int zz = (t / tiles_m) / tiles_n;
+        const int zz = t / (tiles_m * tiles_n);
         const int kb0 = KIND == EPI_PART ? zz * p.kb_per_split : 0;
         const int num_kb = KIND == EPI_PART ? min(p.kb_per_split, total_kb - kb0) : total_kb;
         mbar_wait(&acc_empty[as], aphase ^ 1);   // epilogue has drained this accumulator stage
@@ -285,7 +304,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     pdl_wait();   // the residual / output buffers belong to the preceding kernels
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int tile_m = t % tiles_m, r = t / tiles_m, tile_n = r % tiles_n, zz = r / tiles_n;
+      int tile_m, tile_n, zz;
+        tile_decode(p, t, tiles_m, tiles_n, tile_m, tile_n, zz);
       const int z = KIND == EPI_PART ? 0 : zz, split = KIND == EPI_PART ? zz : 0;
       const int i1 = z % p.zn1, i2 = z / p.zn1;
       mbar_wait(&acc_full[as], aphase);
@@ -483,6 +503,8 @@ static GemmKParams make_params(const GemmOperand& A, const GemmOperand& B, int M
   p.e = epi;
   p.vec_ok = 0;
   p.accum = 0;
+  // B (N x K halves) small enough to live in L2 while A is larger than B: sweep n fastest
+  p.n_fastest = (zb == 1 && (long)N * K * 2 <= (24L << 20) && (long)M * K > (long)N * K) ? 1 : 0;
   p.kb_per_split = 0;
   if (epi.mode == GEMM_STORE && epi.ldn == 1) {
     const int a = epi.out_f32 ? 4 : 8;  // elements per 16 bytes

@@ -112,7 +112,7 @@ void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& 
 struct CrossAttnWorkspace {
   float* part;     // [B][H][nsplit][MAX_ROWS_PER_STREAM][66]  (m, l, o[64])
   float* probs;    // optional [R][H][1500] f32 attention probabilities (align mode) or nullptr
-  int* counters;   // [B][H] arrival counters (zero between launches): the last CTA of a (stream, head) merges the partials
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // profiling: recorded right before / after the main kernel when set
 };
 void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& q, const __half* kc, const __half* vc,
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,

@@ -167,6 +167,10 @@ class B200Whisper:
     def last_device_ms(self, which: int) -> float:
         return float(self.lib.wl_last_device_ms(self.ctx, which))
 
+    def profile_cross_attn(self, enable: bool) -> None:
+        """Bracket every cross-attention launch of graph-less generate calls with CUDA events (bench.py roofline)."""
+        _lib.check(self.lib, self.ctx, self.lib.wl_profile_cross_attn(self.ctx, int(bool(enable))), "wl_profile_cross_attn")
+
     @staticmethod
     def _release_slots(engine_ref, slots):
         eng = engine_ref()
