@@ -69,3 +69,58 @@ def test_batched_equals_single():
 def test_empty_audio_returns_none():
     m = _model(SCENARIOS["en_silence"])
     assert m.transcribe(np.zeros(0, np.float32)) == (None, None)
+
+
+# ------------------------------------------------------------------ N1: on-disk formats either side of create_model
+def test_ct2_model_bin_round_trip(tmp_path):
+    """model.bin writer -> reader gives back the canonical HF-named weights (fp16 rounding only); the tied output
+    projection travels as an alias; k_proj biases (absent in Whisper) do not appear.  Format restated from memory of
+    ctranslate2's ModelSpec._serialize -- this pins self-consistency, not agreement with a real converter."""
+    import torch
+    from whisperlive_b200 import ct2_format
+    from whisperlive_b200.config import dims_for
+    from whisperlive_b200.weights import infer_dims, load_model_dir, random_init
+
+    dims = dims_for("micro")
+    w = random_init(dims, seed=3)
+    d = tmp_path / "ct2"
+    d.mkdir()
+    ct2_format.save_ct2_model_bin(w, str(d / "model.bin"))
+    (d / "config.json").write_text('{"alignment_heads": [[1, 0], [1, 1]], "lang_ids": [5, 6], "suppress_ids": [1, 2]}')
+    variables, aliases, header = ct2_format.read_variables(str(d / "model.bin"))
+    assert header == {"spec": "WhisperSpec", "revision": 3, "version": 6}
+    assert aliases == {"decoder/projection/weight": "decoder/embeddings/weight"}
+    assert variables["encoder/layer_0/self_attention/linear_0/weight"].shape == (3 * dims.d_model, dims.d_model)
+    assert variables["decoder/layer_0/attention/linear_1/weight"].shape == (2 * dims.d_model, dims.d_model)
+    back = load_model_dir(str(d))
+    assert set(back) == {k for k in w if not k.endswith("k_proj.bias")}
+    for k, t in back.items():
+        assert t.dtype == torch.float32
+        torch.testing.assert_close(t, w[k].half().float(), rtol=0, atol=0)
+    got = infer_dims(back, "micro-from-ct2")
+    assert (got.d_model, got.enc_layers, got.dec_layers, got.n_mels, got.vocab) == \
+        (dims.d_model, dims.enc_layers, dims.dec_layers, dims.n_mels, dims.vocab)
+    assert ct2_format.read_ct2_config(str(d))["alignment_heads"] == [(1, 0), (1, 1)]
+
+
+def test_ct2_model_bin_rejects_what_it_does_not_understand(tmp_path):
+    import struct
+
+    import numpy as np
+    import pytest
+    from whisperlive_b200 import ct2_format
+
+    p = tmp_path / "model.bin"
+    p.write_bytes(struct.pack("<I", 5))
+    with pytest.raises(ValueError, match="binary version 5"):
+        ct2_format.read_variables(str(p))
+    ct2_format.write_variables(str(p), {"encoder/conv1/weight": np.zeros((2, 2, 3), np.int8)}, spec="WhisperSpec")
+    with pytest.raises((ValueError, KeyError)):
+        ct2_format.load_ct2_model_bin(str(p))
+    ct2_format.write_variables(str(p), {"x": np.zeros((2,), np.float32)}, spec="TransformerSpec")
+    with pytest.raises(ValueError, match="not a WhisperSpec"):
+        ct2_format.load_ct2_model_bin(str(p))
+    with open(p, "ab") as f:
+        f.write(b"junk")
+    with pytest.raises(ValueError, match="trailing bytes"):
+        ct2_format.read_variables(str(p))

@@ -115,12 +115,18 @@ class B200Whisper:
     @classmethod
     def from_model(cls, model_size_or_path: str, device_index=0, compute_type="float16", weights=None, seed: int = 0,
                    max_streams: int = 8, max_beam: int = 5, **kw) -> "B200Whisper":
-        """Size name -> architecture; weights from ``weights`` (dict), a safetensors directory, or --
-        because no checkpoint exists offline -- seeded random initialisation of that architecture."""
+        """Size name -> architecture; weights from ``weights`` (dict), a model directory -- HF ``model.safetensors``
+        or the CTranslate2 ``model.bin`` the reference's download_model fetches -- or, because no checkpoint exists
+        offline, seeded random initialisation of that architecture."""
         import os
         from . import weights as W
         if weights is None and isinstance(model_size_or_path, str) and os.path.isdir(model_size_or_path):
-            weights = W.load_safetensors(model_size_or_path)
+            weights = W.load_model_dir(model_size_or_path)
+            if "alignment_heads" not in kw or kw["alignment_heads"] is None:
+                from .ct2_format import read_ct2_config
+                heads = read_ct2_config(model_size_or_path).get("alignment_heads")
+                if heads:
+                    kw["alignment_heads"] = heads
         if weights is not None:
             try:
                 dims = dims_for(model_size_or_path)

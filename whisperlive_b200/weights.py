@@ -113,6 +113,17 @@ def load_safetensors(path: str) -> Dict[str, torch.Tensor]:
     return out
 
 
+def load_model_dir(path: str) -> Dict[str, torch.Tensor]:
+    """A model directory in either format the reference's users have on disk: HF ``model.safetensors``
+    (openai/whisper-*) or CTranslate2 ``model.bin`` (Systran/faster-whisper-*; ct2_format.py)."""
+    if os.path.exists(os.path.join(path, "model.safetensors")):
+        return load_safetensors(path)
+    if os.path.exists(os.path.join(path, "model.bin")):
+        from .ct2_format import load_ct2_model_bin
+        return load_ct2_model_bin(path)
+    raise FileNotFoundError(f"{path}: neither model.safetensors nor model.bin")
+
+
 def infer_dims(weights: Dict[str, torch.Tensor], name: str = "custom") -> WhisperDims:
     d = weights["model.encoder.conv1.weight"].shape[0]
     n_mels = weights["model.encoder.conv1.weight"].shape[1]
