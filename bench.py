@@ -280,6 +280,9 @@ def main():
     for _ in range(args.steps):
         dt, n_ids = e2e_step()
         lat.append(dt)
+        if os.environ.get("WLB200_TRACE") and rank == 0:
+            print("e2e step %.1f ms; host split (ms): %s" % (1000 * dt, {k: round(1000 * v, 1) for k, v in model.last_timing.items()}),
+                  file=sys.stderr)
     barrier()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -48,6 +48,7 @@ struct wl_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms[3] = {0, 0, 0};
   // per-kernel profiling of the dominant decode kernel (bench.py roofline): events around every cross-attention launch
+  unsigned* post_bar = nullptr;   // grid-barrier words of the fused split-K consumers
   int prof_cross = 0;
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;
   double prof_cross_ms = 0.0;
@@ -429,6 +430,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
   c->xws.part = dalloc<float>(c, (size_t)c->Bm * H * 12 * MAX_ROWS_PER_STREAM * 66);
   c->xws.probs = nullptr;
+  c->post_bar = dalloc<unsigned>(c, 2);
   c->suppress_mask = dalloc<unsigned>(c, (V + 31) / 32 + 1);
   if (!c->align_heads.empty()) {
     c->align_heads_dev = dalloc<int>(c, c->align_heads.size());
@@ -685,7 +687,13 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   // SMs; every K range stores its raw fp32 partial sum and the CONSUMER (LayerNorm, attention, GELU) adds the
   // ranges and the bias in a fixed order -- no atomics, bit-reproducible, and no separate reduction kernel.
   // part1 holds activations (qkv, q_cross, fc1), part2 the residual updates (out-proj, fc2) until the next LayerNorm.
-  auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias) -> PartialSrc {
+  // WLB200_FUSE_POST (default on): the LayerNorm-update after out-proj / FC2 and the GELU-cast after FC1 run inside
+  // the producing split-K GEMM, behind a grid barrier, instead of as separate kernels (13 -> 9 launches per layer).
+  static const bool fuse_env = [] { const char* e = getenv("WLB200_FUSE_POST"); return e ? atoi(e) != 0 : true; }();
+  static const bool simt_env = [] { const char* e = getenv("WLB200_GEMM_SIMT"); return e && atoi(e) != 0; }();
+  const bool fuse = fuse_env && splitk && !simt_env;
+  struct Post { int kind = GEMM_POST_NONE; const float* g = nullptr; const float* b = nullptr; };
+  auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias, Post post) -> PartialSrc {
     GemmEpilogue e;
     e.out = buf; e.out_f32 = 1; e.ldn = n_out; e.ldm = 1;
     e.a_static = 1;
@@ -697,19 +705,28 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     } else {
       ps.nsplit = 1;   // single pass, bias still added by the consumer
     }
+    if (post.kind != GEMM_POST_NONE) {
+      e.post = post.kind;
+      e.post_bias = bias;
+      e.post_bar = c->post_bar;
+      if (post.kind == GEMM_POST_LN) { e.post_x = c->dx; e.post_g = post.g; e.post_b = post.b; e.post_y = c->dxn; }
+      else e.post_y = c->dh;
+    }
     gemm_tn(st, opnd(W, n_out, K, K), opnd(X, R, K, K), n_out, R, K, e);
     return ps;
   };
-  PartialSrc pending;   // residual update not yet folded into x
+  auto ln_post = [&](const float* g, const float* b) { Post p; if (fuse) { p.kind = GEMM_POST_LN; p.g = g; p.b = b; } return p; };
+  PartialSrc pending;   // residual update not yet folded into x (unfused path)
   for (int l = 0; l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
-    const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv);
+    const bool last = l + 1 == c->Ld;
+    if (!fuse || l == 0) layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv, Post());
     decoder_self_attn(st, s, qkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
-    pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o);
-    layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
-    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc);
+    pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o, ln_post(L.ln2_g, L.ln2_b));
+    if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
+    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc, Post());
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -726,13 +743,17 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     }
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
-    pending = part_gemm(L.w_oc, d, d, c->datt, c->part2, L.b_oc);
-    layernorm_update_rows(st, c->dx, pending, L.ln3_g, L.ln3_b, c->dxn, R, d);
-    const PartialSrc h1 = part_gemm(L.w_fc1, ff, d, c->dxn, c->part1, L.b_fc1);
-    gelu_cast(st, h1, c->dh, R, ff);
-    pending = part_gemm(L.w_fc2, d, ff, c->dh, c->part2, L.b_fc2);
+    pending = part_gemm(L.w_oc, d, d, c->datt, c->part2, L.b_oc, ln_post(L.ln3_g, L.ln3_b));
+    if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln3_g, L.ln3_b, c->dxn, R, d);
+    Post gp;
+    if (fuse) gp.kind = GEMM_POST_GELU;
+    const PartialSrc h1 = part_gemm(L.w_fc1, ff, d, c->dxn, c->part1, L.b_fc1, gp);
+    if (!fuse) gelu_cast(st, h1, c->dh, R, ff);
+    // FC2's fused LayerNorm is the NEXT layer's ln1 (or the final LayerNorm after the last layer)
+    pending = part_gemm(L.w_fc2, d, ff, c->dh, c->part2, L.b_fc2,
+                        last ? ln_post(c->lnf_g, c->lnf_b) : ln_post(c->dec[l + 1].ln1_g, c->dec[l + 1].ln1_b));
   }
-  layernorm_update_rows(st, c->dx, pending, c->lnf_g, c->lnf_b, c->dxn, R, d);
+  if (!fuse) layernorm_update_rows(st, c->dx, pending, c->lnf_g, c->lnf_b, c->dxn, R, d);
   {
     GemmEpilogue e;
     e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;

@@ -148,6 +148,126 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, long m, int
   }
 }
 
+// Sense-reversing grid barrier for a grid whose CTAs are all resident; called by ONE thread per CTA.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  const unsigned gen = ld_acquire_u32(bar + 1);
+  __threadfence();
+  if (atomicAdd(bar, 1u) == nblocks - 1u) {
+    atomicExch(bar, 0u);
+    __threadfence();
+    atomicAdd(bar + 1, 1u);
+  } else {
+    while (ld_acquire_u32(bar + 1) == gen) __nanosleep(20);
+  }
+  __threadfence();
+}
+template <int NT>
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory"); }
+
+// Row-wise consumer of the split-K partial sums, run by the NT epilogue threads of every CTA after the grid barrier
+// (same arithmetic, in the same order, as layernorm_update_kernel / gelu_cast_kernel).
+template <int NT>
+__device__ __forceinline__ void post_op(const GemmKParams& p, int te, float* red /*[16]*/) {
+  const GemmEpilogue& e = p.e;
+  const int S = e.partials, R = p.N, F = p.M;   // K ranges, rows, features
+  const float* part = reinterpret_cast<const float*>(e.out);
+  if (e.post == GEMM_POST_LN) {
+    const int n4 = F >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(e.post_g);
+    const float4* b4 = reinterpret_cast<const float4*>(e.post_b);
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+      float4* x4 = reinterpret_cast<float4*>(e.post_x + (long)r * F);
+      constexpr int PER = 3;   // float4 per thread: d <= 4 * PER * NT
+      float4 v[PER];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = i * NT + te;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n4) {
+          if (e.post_bias) v[i] = __ldg(reinterpret_cast<const float4*>(e.post_bias) + c);
+          const float4 a = x4[c];
+          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+        }
+      }
+#pragma unroll 8
+      for (int sp = 0; sp < S; ++sp) {
+        const float4* p4 = reinterpret_cast<const float4*>(part + (long)sp * e.part_stride + (long)r * F);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int c = i * NT + te;
+          if (c < n4) {
+            const float4 q = __ldcg(p4 + c);
+            v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = i * NT + te;
+        if (c < n4) x4[c] = v[i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      sum = warp_sum(sum);
+      if ((te & 31) == 0) red[te >> 5] = sum;
+      epi_sync<NT>();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) tot += red[w];
+      const float mean = tot / F;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        if (i * NT + te < n4) {
+          const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+          sq += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+        }
+      }
+      sq = warp_sum(sq);
+      if ((te & 31) == 0) red[8 + (te >> 5)] = sq;
+      epi_sync<NT>();
+      float tq = 0.f;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) tq += red[8 + w];
+      const float rstd = rsqrtf(tq / F + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = i * NT + te;
+        if (c < n4) {
+          const float4 gg = g4[c], bb = b4[c];
+          __align__(8) __half2 h[2] = {
+              __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+              __floats2half2_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w)};
+          *reinterpret_cast<uint2*>(e.post_y + (long)r * F + 4 * c) = *reinterpret_cast<const uint2*>(h);
+        }
+      }
+      epi_sync<NT>();   // red is reused by the next row
+    }
+  } else if (e.post == GEMM_POST_GELU) {
+    const int c4n = F >> 2;
+    const long total4 = (long)R * c4n;
+    const long st4 = e.part_stride >> 2;
+    for (long i4 = (long)blockIdx.x * NT + te; i4 < total4; i4 += (long)gridDim.x * NT) {
+      const int c = (int)(i4 % c4n);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.post_bias) v = __ldg(reinterpret_cast<const float4*>(e.post_bias) + c);
+      const float4* p4 = reinterpret_cast<const float4*>(part) + i4;
+#pragma unroll 4
+      for (int sp = 0; sp < S; ++sp) {
+        const float4 q = __ldcg(p4 + sp * st4);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      __align__(8) __half2 h[2] = {__floats2half2_rn(gelu_erf(v.x), gelu_erf(v.y)), __floats2half2_rn(gelu_erf(v.z), gelu_erf(v.w))};
+      *reinterpret_cast<uint2*>(e.post_y + 4 * i4) = *reinterpret_cast<const uint2*>(h);
+    }
+  }
+}
+
 // Tile order inside one batch entry.  m fastest: CTAs running side by side share the B tile (right when B is the big
 // operand).  n fastest (p.n_fastest): they share the A tile and sweep B -- right when B is a weight matrix that stays
 // in L2 anyway and A is a large activation (FC2 of the encoder: A = 123 MB would otherwise be re-read per n tile).
@@ -184,6 +304,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = empty + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* post_red = reinterpret_cast<float*>(tmem_slot + 2);   // [16]
 
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -354,6 +475,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if constexpr (KIND == EPI_PART) {
+      if (p.e.post != GEMM_POST_NONE) {
+        constexpr int NT = BN >= 64 ? 256 : 128;   // epilogue threads of this configuration
+        const int te = threadIdx.x - 128;
+        __threadfence();                           // this thread's partial sums are visible device-wide
+        epi_sync<NT>();
+        if (te == 0) grid_barrier(p.e.post_bar, gridDim.x);
+        epi_sync<NT>();
+        post_op<NT>(p, te, post_red);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -439,7 +571,7 @@ static TmapInfo get_tmap(const GemmOperand& op, int box_rows, int box_k) {
 
 template <int BN, int STAGES, int MIN_CTAS, int KIND>
 static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int Z) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 512;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   GemmKParams q = p;
@@ -452,7 +584,7 @@ static void launch_cfg(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
 
 template <int BN, int STAGES, int MIN_CTAS, int KIND>
 static void prime_cfg() {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 512;
   WL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, MIN_CTAS, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
@@ -551,6 +683,16 @@ void gemm_tn(cudaStream_t stream, const GemmOperand& A, const GemmOperand& B, in
   if (epi.partials > 0) {
     WL_CHECK(Z == 1 && epi.out_f32 && !epi.gelu && !epi.resid && !epi.bias && epi.mode == GEMM_STORE, WL_ERR_ARG,
              "gemm_tn: split-K partial output must be plain fp32 without bias");
+  } else {
+    WL_CHECK(epi.post == GEMM_POST_NONE, WL_ERR_ARG, "gemm_tn: a fused post-op needs the split-K partial output");
+  }
+  if (epi.partials > 0) {
+    if (epi.post != GEMM_POST_NONE) {
+      WL_CHECK(epi.post_bar && epi.post_y && M % 4 == 0 && epi.part_stride % 4 == 0 && epi.ldm == 1 && epi.ldn == M, WL_ERR_ARG,
+               "gemm_tn: fused post-op needs the [range][row][feature] partial layout");
+      WL_CHECK(epi.post != GEMM_POST_LN || (epi.post_x && epi.post_g && epi.post_b && M <= 4 * 3 * 128), WL_ERR_ARG,
+               "gemm_tn: fused LayerNorm supports rows of at most 1536 features");
+    }
     const int total_kb = cdiv(K, BK);
     p.accum = 1;
     p.kb_per_split = cdiv(total_kb, epi.partials);

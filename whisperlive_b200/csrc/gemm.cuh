@@ -18,6 +18,8 @@ struct GemmOperand {
   long s2 = 0;
 };
 
+enum GemmPost : int { GEMM_POST_NONE = 0, GEMM_POST_LN = 1, GEMM_POST_GELU = 2 };
+
 enum GemmMode : int {
   GEMM_STORE = 0,      // out[z][m*ldm + n*ldn]
   GEMM_HEADSPLIT = 1,  // cross-KV cache layout: row m=(b,s), col n=(h,dd) -> out[slot[b]][h][s][dd]
@@ -35,6 +37,17 @@ struct GemmEpilogue {
   long rldm = 0, rldn = 1, rb1 = 0, rb2 = 0;
   int partials = 0;          // >0: split K into `partials` ranges; range s stores its raw fp32 partial sum at
   long part_stride = 0;      //     out + s*part_stride (no bias); the consumer adds them in order (deterministic)
+  // Fused consumer of a split-K result (partials > 0 only): after its partial stores every CTA passes a grid-wide
+  // barrier (all CTAs are resident: the kernel is persistent) and the epilogue warps run the row-wise operation that
+  // would otherwise be the next kernel.  GEMM_POST_LN: x[r] += bias + sum_s partial_s[r]; y[r] = LayerNorm(x[r]) (fp16).
+  // GEMM_POST_GELU: y = gelu(bias + sum_s partial_s) (fp16).  Rows are the GEMM's n index (swap-AB), features its m.
+  int post = 0;
+  float* post_x = nullptr;
+  const float* post_bias = nullptr;
+  const float* post_g = nullptr;
+  const float* post_b = nullptr;
+  __half* post_y = nullptr;
+  unsigned* post_bar = nullptr;   // {arrival count, generation}, zero-initialised, one pair per context
   int a_static = 0;          // A is a weight matrix: under programmatic dependent launch its first k-blocks are
                              //     fetched before waiting for the preceding kernel (which only produces B)
   int mode = GEMM_STORE;

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import itertools
 import json
+import time
 import logging
 import os
 import zlib
@@ -521,7 +522,10 @@ class B200WhisperModel:
         kws = list(per_stream_kwargs) if per_stream_kwargs is not None else [{} for _ in range(n)]
         results: List[Any] = [None] * n
         jobs: List[Tuple[int, _StreamJob, dict]] = []
+        tm = self.last_timing = {"prepare": 0.0, "mel": 0.0, "encode": 0.0, "generate": 0.0, "host_decode": 0.0, "finish": 0.0}
+        t0 = time.perf_counter()
         prepared = [self._prepare_stream(np.asarray(a), dict(k)) for a, k in zip(audios, kws)]
+        tm["prepare"] = time.perf_counter() - t0
         # mel for all non-empty streams in one device call
         live = [i for i, p in enumerate(prepared) if p is not None]
         for i in range(n):
@@ -529,8 +533,10 @@ class B200WhisperModel:
                 results[i] = (None, None)
         if not live:
             return results
+        t0 = time.perf_counter()
         feats = self.feature_extractor.batch([prepared[i]["audio"] for i in live],
                                              chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
+        tm["mel"] = time.perf_counter() - t0
         for i, f in zip(live, feats):
             prepared[i]["features"] = f
         self._resolve_languages([prepared[i] for i in live])
@@ -543,6 +549,7 @@ class B200WhisperModel:
             job.single_window = p["single_window"]
             jobs.append((i, job, p))
         self._run_jobs([j for _, j, _ in jobs])
+        t0 = time.perf_counter()
         for i, job, p in jobs:
             segs = job.segments
             if p["speech_chunks"]:
@@ -553,6 +560,7 @@ class B200WhisperModel:
                                      transcription_options=p["options"], vad_options=p["vad_parameters"],
                                      all_language_probs=p["all_language_probs"])
             results[i] = (segs, info)
+        tm["finish"] = time.perf_counter() - t0
         return results
 
     # -- stream preparation (reference :811-861) --------------------------------------------------
@@ -653,7 +661,10 @@ class B200WhisperModel:
             live = [(j, w) for j, w in windows if w is not None]
             if not live:
                 return
+            tm = getattr(self, "last_timing", None) or {}
+            t0 = time.perf_counter()
             enc = self.encode(np.stack([w for _, w in live]))
+            tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
             for k, (j, _) in enumerate(live):
                 j.enc = enc.select([k]) if hasattr(enc, "select") else _EncoderSlice(enc, k)
                 if j.opt.multilingual:
@@ -678,10 +689,14 @@ class B200WhisperModel:
                         kw["max_length_per_stream"] = lengths
                         kw["max_length"] = max(lengths)
                     sub = enc.select(ks) if hasattr(enc, "select") else _EncoderSlice(enc, ks)
+                    t0 = time.perf_counter()
                     outs = self.model.generate(sub, [live[k][0].prompt for k in ks], **kw)
+                    t1 = time.perf_counter()
                     for k, r in zip(ks, outs):
                         if not live[k][0].accept(r):
                             nxt.append(k)
+                    tm["generate"] = tm.get("generate", 0.0) + t1 - t0
+                    tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
                 pending = sorted(nxt)
             for j, _ in live:
                 j.finish_window()
