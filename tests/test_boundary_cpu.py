@@ -187,3 +187,21 @@ def test_two_rank_stream_sharding_matches_single_process(tmp_path):
     merged = json.loads(line[len("RESULT "):])
     for i, seq in enumerate(single):
         assert [t for t in merged[i] if t >= 0] == seq
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) works without a GPU and prints one JSON line
+    with the contract's keys; a tiny architecture keeps it to seconds."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "micro.en", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "2", "--beam", "2"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-sec/sec" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["steps"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "stand-in" in line["cpu_baseline"]["sample"]
