@@ -1,7 +1,10 @@
-// Decoder attention kernels (fp32 math, fp16 K/V storage).
-//   K10 decoder_self_attn : KV cache append + attention over <=448 positions with beam indirection
-//   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V,
-//       streamed HBM -> smem by a producer warp with cp.async.bulk + mbarrier ring, consumed by 4 warps.
+// Decoder attention kernels (fp16 K/V storage, fp32 accumulation and softmax).
+//   K10 decoder_self_attn : KV cache append + attention over <=448 positions with beam indirection, one warp per
+//       (row, head), CUDA-core math (a few KB of work per warp).
+//   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V -- persistent
+//       CTAs, K/V streamed HBM -> smem by a producer warp (cp.async.bulk + mbarrier ring), consumed by 4 warps with
+//       mma.sync on the pre-swizzled chunks; partial softmaxes per key range merged by a small combine kernel.
+//   Reference call site of both: ctranslate2 Whisper.generate, transcriber_faster_whisper.py:1394-1407.
 #include <algorithm>
 #include <cstdlib>
 #include <map>
