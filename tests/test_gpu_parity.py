@@ -410,3 +410,61 @@ def test_transcribe_end_to_end_matches_oracle_pipeline():
                 assert a.avg_logprob == pytest.approx(b.avg_logprob, abs=0.25)
         else:
             assert gs[0].tokens[:1] == rs[0].tokens[:1] or True
+
+
+# --------------------------------------------------------------------------------------- full size (BASELINE config)
+def test_full_size_large_v3_single_stream():
+    """The architecture BASELINE.json's metric is quoted on (large-v3: d=1280, 20 heads, 32+32 layers, 128 mels,
+    51866 tokens) at a batch the CPU oracle finishes in seconds: one 9 s stream.  Checks K1 (128-mel filterbank),
+    K2-K7 (encoder output), K8-K12 (teacher-forced logits and the beam-4 hypothesis, re-scored by the oracle) and two
+    size-independent properties: batch invariance of the encoder and run-to-run bit-reproducibility of generate
+    (deterministic split-K, no atomics).  Tolerances are wider than at tiny sizes: 32 fp16 layers instead of 4."""
+    import time
+    t0 = time.time()
+    dims = dims_for("large-v3")
+    w = random_init(dims, seed=5)
+    from whisperlive_b200.engine import B200Whisper
+    eng = B200Whisper(dims, w, max_streams=2, max_beam=4, enc_slots=4)
+    orc = OracleWhisper(w, dims)
+    print(f"large-v3 init {time.time() - t0:.1f} s")
+    wav = synth.speech_like(9.0, seed=21)
+    ref_mel = omel.log_mel(wav, dims.n_mels)
+    got_mel = eng.mel([wav])[0]
+    assert got_mel.shape == ref_mel.shape == (128, len(wav) // 160 + 1)
+    assert np.abs(got_mel - ref_mel).max() < 2e-4
+    feats = omel.pad_or_trim(ref_mel[:, :-1])[None]
+    enc = eng.encode(feats)
+    got = np.asarray(enc)
+    t1 = time.time()
+    oenc = orc.encode(feats)
+    ref = oenc.enc.numpy()
+    print(f"oracle encoder {time.time() - t1:.1f} s")
+    err = np.abs(got - ref)
+    rel_rms = float(np.sqrt((err ** 2).mean() / (ref ** 2).mean()))
+    print(f"encoder large-v3: max err {err.max():.4f} mean err {err.mean():.5f} rel rms {rel_rms:.5f} ref mean abs {np.abs(ref).mean():.3f}")
+    assert rel_rms < 0.02 and err.mean() < 0.02 and err.max() < 0.5
+    # batch invariance: the same stream next to a different one gives the same encoder output
+    other = feats_for(dims, 21.0, 22)[None]
+    pair = np.asarray(eng.encode(np.concatenate([other, feats])))
+    assert np.abs(pair[1] - got[0]).max() < 2e-3
+    # teacher-forced logits over a short token sequence
+    rng = np.random.default_rng(8)
+    toks = [[orc.spec.sot] + rng.integers(0, 50000, 5).tolist()]
+    lg = eng.decode_logits(enc, toks)[0]
+    from oracle import model as om
+    with torch.no_grad():
+        ref_lg = om.decoder_forward(orc.w, torch.tensor(toks), oenc.xkv, om.DecoderState(dims.dec_layers), dims.n_heads,
+                                    dims.dec_layers)[0].numpy()
+    lerr = np.abs(lg - ref_lg)
+    print(f"logits large-v3: max err {lerr.max():.4f} mean {lerr.mean():.5f} (logit std {ref_lg.std():.2f})")
+    assert lerr.max() < 4 * LOGIT_TOL and lerr.mean() < LOGIT_TOL / 2
+    # beam-4 generate, a few tokens: the engine's hypothesis, teacher-forced through the oracle, scores what the engine says
+    sot_seq = [orc.spec.sot, orc.spec.sot + 1, orc.spec.sot + 1 + dims.num_languages + 1]
+    kw = dict(beam_size=4, max_length=2 * 8, suppress_tokens=[-1], suppress_blank=True)
+    a = eng.generate(enc, [sot_seq], **kw)[0]
+    b = eng.generate(enc, [sot_seq], **kw)[0]
+    assert a.sequences_ids == b.sequences_ids and a.scores == b.scores, "generate is not bit-reproducible"
+    rescored = _oracle_rescore(orc, oenc, 0, sot_seq, a.sequences_ids[0], kw)
+    print(f"generate large-v3 beam 4: {len(a.sequences_ids[0])} tokens, engine score {a.scores[0]:.4f}, oracle score of the same tokens {rescored:.4f}")
+    assert abs(rescored - a.scores[0]) < 0.06
+    del eng
