@@ -418,7 +418,7 @@ def test_full_size_large_v3_single_stream():
     51866 tokens) at a batch the CPU oracle finishes in seconds: one 9 s stream.  Checks K1 (128-mel filterbank),
     K2-K7 (encoder output), K8-K12 (teacher-forced logits and the beam-4 hypothesis, re-scored by the oracle) and two
     size-independent properties: batch invariance of the encoder and run-to-run bit-reproducibility of generate
-    (deterministic split-K, no atomics).  Tolerances are wider than at tiny sizes: 32 fp16 layers instead of 4."""
+    (deterministic split-K, no atomics)."""
     import time
     t0 = time.time()
     dims = dims_for("large-v3")
@@ -442,7 +442,7 @@ def test_full_size_large_v3_single_stream():
     err = np.abs(got - ref)
     rel_rms = float(np.sqrt((err ** 2).mean() / (ref ** 2).mean()))
     print(f"encoder large-v3: max err {err.max():.4f} mean err {err.mean():.5f} rel rms {rel_rms:.5f} ref mean abs {np.abs(ref).mean():.3f}")
-    assert rel_rms < 0.02 and err.mean() < 0.02 and err.max() < 0.5
+    assert rel_rms < 0.008 and err.mean() < 0.006 and err.max() < 0.06     # measured on B200: 0.0018 / 0.0015 / 0.011
     # batch invariance: the same stream next to a different one gives the same encoder output
     other = feats_for(dims, 21.0, 22)[None]
     pair = np.asarray(eng.encode(np.concatenate([other, feats])))
@@ -457,7 +457,7 @@ def test_full_size_large_v3_single_stream():
                                     dims.dec_layers)[0].numpy()
     lerr = np.abs(lg - ref_lg)
     print(f"logits large-v3: max err {lerr.max():.4f} mean {lerr.mean():.5f} (logit std {ref_lg.std():.2f})")
-    assert lerr.max() < 4 * LOGIT_TOL and lerr.mean() < LOGIT_TOL / 2
+    assert lerr.max() < LOGIT_TOL and lerr.mean() < 0.015                      # measured: 0.024 / 0.0034
     # beam-4 generate, a few tokens: the engine's hypothesis, teacher-forced through the oracle, scores what the engine says
     sot_seq = [orc.spec.sot, orc.spec.sot + 1, orc.spec.sot + 1 + dims.num_languages + 1]
     kw = dict(beam_size=4, max_length=2 * 8, suppress_tokens=[-1], suppress_blank=True)
@@ -466,5 +466,5 @@ def test_full_size_large_v3_single_stream():
     assert a.sequences_ids == b.sequences_ids and a.scores == b.scores, "generate is not bit-reproducible"
     rescored = _oracle_rescore(orc, oenc, 0, sot_seq, a.sequences_ids[0], kw)
     print(f"generate large-v3 beam 4: {len(a.sequences_ids[0])} tokens, engine score {a.scores[0]:.4f}, oracle score of the same tokens {rescored:.4f}")
-    assert abs(rescored - a.scores[0]) < 0.06
+    assert abs(rescored - a.scores[0]) < 0.02                                    # measured: 0.0013
     del eng
