@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import itertools
 import json
+import threading
 import time
 import logging
 import os
@@ -249,6 +250,12 @@ class _StreamJob:
 
     # -- window selection (reference :1104-1127) -------------------------------------------
     def next_window(self) -> Optional[np.ndarray]:
+        """Features of the next 30 s window, zero-padded to 3000 frames (reference :1115-1127), or None at the end."""
+        view = self.advance_window()
+        return None if view is None else pad_or_trim(view, self.m.feature_extractor.nb_max_frames)
+
+    def advance_window(self) -> Optional[np.ndarray]:
+        """Move to the next window and return its un-padded feature view [n_mels, <= 3000]."""
         fe = self.m.feature_extractor
         while self.clip_idx < len(self.clips):
             lo, hi = self.clips[self.clip_idx]
@@ -264,7 +271,7 @@ class _StreamJob:
             self.segment_size = min(fe.nb_max_frames, self.content_frames - self.seek, hi - self.seek)
             self.segment_duration = self.segment_size * fe.time_per_frame
             self.temp_idx, self.tried, self.below_cr = 0, [], []
-            return pad_or_trim(self.features[:, self.seek:self.seek + self.segment_size], fe.nb_max_frames)
+            return self.features[:, self.seek:self.seek + min(self.segment_size, fe.nb_max_frames)]
         return None
 
     def build_prompt(self) -> List[int]:
@@ -657,13 +664,13 @@ class B200WhisperModel:
     def _run_jobs(self, jobs: List[_StreamJob]) -> None:
         """Advance all streams window by window; every device call covers every live stream."""
         while True:
-            windows = [(j, j.next_window()) for j in jobs]
+            windows = [(j, j.advance_window()) for j in jobs]
             live = [(j, w) for j, w in windows if w is not None]
             if not live:
                 return
             tm = getattr(self, "last_timing", None) or {}
             t0 = time.perf_counter()
-            enc = self.encode(np.stack([w for _, w in live]))
+            enc = self.encode(self._stack_windows([w for _, w in live]))
             tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
             for k, (j, _) in enumerate(live):
                 j.enc = enc.select([k]) if hasattr(enc, "select") else _EncoderSlice(enc, k)
@@ -704,6 +711,24 @@ class B200WhisperModel:
                 if j.single_window:
                     j.seek = j.content_frames     # bench switch: one 30 s window per chunk (pinned work)
             del enc
+
+    def _stack_windows(self, views: List[np.ndarray]) -> np.ndarray:
+        """[B, n_mels, 3000] batch of zero-padded windows, written straight into a buffer that is reused from call to
+        call (the 49 MB batch of 32 large-v3 windows is otherwise allocated, page-faulted and copied twice per step:
+        np.pad per stream, then np.stack).  The engine consumes the batch before encode() returns, and the buffer is
+        per thread, so nothing else can touch it in between."""
+        fe = self.feature_extractor
+        n_frames, n_mels = fe.nb_max_frames, views[0].shape[0]
+        tls = self.__dict__.setdefault("_win_tls", threading.local())   # one buffer per calling thread: no sharing
+        buf = getattr(tls, "buf", None)
+        if buf is None or buf.shape[0] < len(views) or buf.shape[1] != n_mels or buf.shape[2] != n_frames:
+            buf = tls.buf = np.zeros((len(views), n_mels, n_frames), dtype=np.float32)
+        out = buf[:len(views)]
+        for k, v in enumerate(views):
+            t = v.shape[1]
+            out[k, :, :t] = v
+            out[k, :, t:] = 0.0
+        return out
 
     def generate_segments(self, features: np.ndarray, tokenizer: Tokenizer, options: TranscriptionOptions,
                           log_progress=False, encoder_output=None) -> List[Segment]:
