@@ -206,6 +206,8 @@ extern "C" void wl_destroy(wl_ctx* c) {
   if (c->h_flt) cudaFreeHost(c->h_flt);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->pev0) cudaEventDestroy(c->pev0);
+  if (c->pev1) cudaEventDestroy(c->pev1);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
