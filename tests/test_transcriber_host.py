@@ -124,3 +124,32 @@ def test_ct2_model_bin_rejects_what_it_does_not_understand(tmp_path):
         f.write(b"junk")
     with pytest.raises(ValueError, match="trailing bytes"):
         ct2_format.read_variables(str(p))
+
+
+def test_window_batch_buffer_equals_pad_and_stack():
+    """_stack_windows (reused per-thread buffer) gives exactly np.stack(pad_or_trim(view)) -- including after a larger
+    batch left stale data in the buffer, and independently per thread."""
+    import threading
+
+    import numpy as np
+    from whisperlive_b200.transcriber import pad_or_trim
+
+    m = _model(next(iter(SCENARIOS.values())))
+    n_mels = m.feature_extractor.mel_filters.shape[0] if hasattr(m.feature_extractor, "mel_filters") else 80
+    rng = np.random.default_rng(0)
+
+    def views(lengths):
+        return [rng.standard_normal((n_mels, t)).astype(np.float32) for t in lengths]
+
+    big = views([3000, 17, 1234, 2999])
+    got = m._stack_windows(big).copy()
+    assert got.shape == (4, n_mels, 3000) and got.flags.c_contiguous
+    np.testing.assert_array_equal(got, np.stack([pad_or_trim(v, 3000) for v in big]))
+    small = views([5, 300])                                  # shorter windows over the stale rows of the previous batch
+    got2 = m._stack_windows(small)
+    assert got2.flags.c_contiguous
+    np.testing.assert_array_equal(got2, np.stack([pad_or_trim(v, 3000) for v in small]))
+    other = {}
+    t = threading.Thread(target=lambda: other.setdefault("buf", m._stack_windows(views([10]))))
+    t.start(); t.join()
+    assert not np.shares_memory(other["buf"], got2)          # a second thread never sees this thread's buffer
