@@ -153,3 +153,19 @@ def test_window_batch_buffer_equals_pad_and_stack():
     t = threading.Thread(target=lambda: other.setdefault("buf", m._stack_windows(views([10]))))
     t.start(); t.join()
     assert not np.shares_memory(other["buf"], got2)          # a second thread never sees this thread's buffer
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/whisper_live"), reason="reference tree only exists in the build container")
+def test_host_helpers_match_reference_code_live():
+    """Differential run against the reference's own functions (imported with ctranslate2 / faster_whisper stubbed) on
+    ~1400 randomised inputs: timestamp splitting, prompt assembly, suppress list, punctuation merge, compression ratio."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "diff_reference_host.py")], capture_output=True,
+                         text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["cases"] > 1000 and res["n_mismatch"] == 0, res["mismatches"]
