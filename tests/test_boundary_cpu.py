@@ -205,3 +205,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["steps"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "stand-in" in line["cpu_baseline"]["sample"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/whisper_live"), reason="reference tree only exists in the build container")
+def test_reference_batcher_runs_unmodified_on_the_b200_transcriber():
+    """the reference's own BatchInferenceWorker (batch_inference.py:193-438), imported from the
+    reference tree, driven once over B200WhisperModel and once over the reference's WhisperModel (same CPU oracle engine
+    underneath) -- every request completes without error and the two runs agree segment for segment (tokens, times,
+    avg_logprob, no_speech_prob, temperature, language), for the batched path and the batch-of-one path."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "run_reference_batcher.py")], capture_output=True,
+                         text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert set(res) == {"micro.en", "micro"}
+    for name, v in res.items():
+        mine, theirs = v["over_b200_model"], v["over_reference_model"]
+        assert len(mine) == 4 and all(r["error"] is None and r["done"] for r in mine), (name, mine)
+        assert all(r["segments"] for r in mine) and all(r["segment_type"] == "Segment" for r in mine)
+        assert mine == theirs, name
