@@ -5,6 +5,7 @@ whisper_live/transcriber/transcriber_faster_whisper.py with the same sys.modules
 make_golden_transcribe.py and calls, side by side with whisperlive_b200.transcriber,
     _split_segments_by_timestamps (:970-1047)   get_prompt (:1480-1513)
     get_suppressed_tokens (:1831-1853)          merge_punctuations (:1856-1887)      get_compression_ratio (:1826-1828)
+    detect_language (:1716-1789, multilingual model: first-segment threshold and majority vote)
 Prints one JSON object {"cases": n, "mismatches": [...]}; tests/test_transcriber_host.py asserts the list is empty.
 Executed in its own process because the stubs (fake ctranslate2 / faster_whisper modules) must not leak into pytest.
 """
@@ -79,6 +80,18 @@ def main():
             n += 1
             if (None if a is None else tuple(a)) != (None if b is None else tuple(b)):
                 bad.append(("get_suppressed_tokens", model_name, sup))
+        # ---- detect_language wrapper (:1716-1789): threshold hit on the first segment, and the majority-vote path
+        if dims.multilingual:
+            from whisperlive_b200 import synth
+            for sec, nseg, thr in ((7.0, 1, 0.5), (41.0, 2, 0.999), (65.0, 3, 0.0)):
+                audio = synth.speech_like(sec, seed=int(sec))
+                a = rm.detect_language(audio=audio, language_detection_segments=nseg, language_detection_threshold=thr)
+                b = om.detect_language(audio=audio, language_detection_segments=nseg, language_detection_threshold=thr)
+                n += 1
+                same = a[0] == b[0] and abs(a[1] - b[1]) < 1e-6 and [x[0] for x in a[2]] == [x[0] for x in b[2]] and \
+                    all(abs(x[1] - y[1]) < 1e-6 for x, y in zip(a[2], b[2]))
+                if not same:
+                    bad.append(("detect_language", sec, nseg, thr, a[:2], b[:2]))
     # ---- merge_punctuations / get_compression_ratio (tokenizer independent)
     words = ["hello", " world", " \"", "quoted", ",", " and", " (", "paren", ")", ".", " ¿", "que", "?", " -", "dash", "!"]
     for _ in range(300):
