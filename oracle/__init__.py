@@ -15,7 +15,13 @@ Pinning status (see DESIGN.md "Oracle"):
   * host logic     -- pinned against the reference's own
                       transcriber_faster_whisper.py executed with stubbed
                       ctranslate2/faster_whisper imports; fixtures in tests/golden/.
-  * CT2 search / timestamp rules / align -- **parity unpinned**: CTranslate2 and
-                      faster-whisper are not installed and not vendored in
-                      /root/reference; restated from their published algorithm.
+  * CT2 search / timestamp rules / align -- **parity unpinned** at the CTranslate2
+                      boundary: CTranslate2 and faster-whisper are not installed and
+                      not vendored in /root/reference; restated from their published
+                      algorithm.  Closest executable anchors (tests/test_oracle_golden.py):
+                      the logits rules (suppress list, suppress-blank, timestamp rules,
+                      log-softmax), the median filter, DTW and the alignment pipeline
+                      order agree exactly with transformers' ports of OpenAI whisper's
+                      ApplyTimestampRules / timing.py -- the code CTranslate2 itself ports.
+                      The beam search proper (CT2 decoding.cc) has no such anchor.
 """
