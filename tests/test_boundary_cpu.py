@@ -224,3 +224,18 @@ def test_reference_batcher_runs_unmodified_on_the_b200_transcriber():
         assert len(mine) == 4 and all(r["error"] is None and r["done"] for r in mine), (name, mine)
         assert all(r["segments"] for r in mine) and all(r["segment_type"] == "Segment" for r in mine)
         assert mine == theirs, name
+
+
+def test_bench_reference_arm_under_torchrun_two_ranks():
+    """The driver launches the reference arm like ours for N > 1: rank 0 alone measures and prints the line, the other
+    ranks exit 0 without work."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--model", "micro.en",
+           "--steps", "1", "--warmup", "0", "--cpu-seconds", "2", "--beam", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
