@@ -169,3 +169,30 @@ def test_host_helpers_match_reference_code_live():
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["cases"] > 1000 and res["n_mismatch"] == 0, res["mismatches"]
+
+
+def test_ct2_model_bin_reads_bfloat16_payloads(tmp_path):
+    """dtype id 5 (bfloat16) is widened to float32 on read; a hand-assembled record exercises that branch and aliases."""
+    import struct
+
+    import numpy as np
+    from whisperlive_b200 import ct2_format
+
+    vals = np.array([[1.0, -2.5, 0.15625], [3.0e4, -1.0e-3, 0.0]], dtype=np.float32)
+    bf16 = (vals.view(np.uint32) >> 16).astype(np.uint16)          # truncation: exact for these values' top 16 bits
+
+    def wstr(s):
+        b = s.encode()
+        return struct.pack("<H", len(b) + 1) + b + b"\0"
+
+    blob = struct.pack("<I", 6) + wstr("WhisperSpec") + struct.pack("<II", 3, 1)
+    blob += wstr("decoder/embeddings/weight") + struct.pack("<B", 2) + struct.pack("<II", 2, 3) + struct.pack("<BI", 5, bf16.nbytes)
+    blob += bf16.tobytes() + struct.pack("<I", 1) + wstr("decoder/projection/weight") + wstr("decoder/embeddings/weight")
+    p = tmp_path / "model.bin"
+    p.write_bytes(blob)
+    variables, aliases, header = ct2_format.read_variables(str(p))
+    got = variables["decoder/embeddings/weight"]
+    assert got.dtype == np.float32 and got.shape == (2, 3)
+    expect = (bf16.astype(np.uint32) << 16).view(np.float32).reshape(2, 3)
+    np.testing.assert_array_equal(got, expect)
+    assert abs(got[0, 1] + 2.5) < 1e-6 and aliases == {"decoder/projection/weight": "decoder/embeddings/weight"}
