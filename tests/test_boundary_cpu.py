@@ -50,6 +50,24 @@ def test_product_never_imports_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
 
 
+def test_no_silent_random_weights_or_synthetic_tokenizer(tmp_path):
+    """a size name without a checkpoint must raise (the reference resolves it through the hub,
+    faster_whisper_backend.py:133-178); random weights / the fabricated vocabulary are explicit opt-ins only."""
+    from whisperlive_b200.engine import B200Whisper
+    from whisperlive_b200.transcriber import B200WhisperModel
+    with pytest.raises(FileNotFoundError, match="no checkpoint"):
+        B200Whisper.from_model("small.en", local_files_only=True, download_root=str(tmp_path))
+    with pytest.raises(ValueError):
+        B200Whisper.from_model("small.en", weights="zeros")
+    with pytest.raises(FileNotFoundError, match="no checkpoint"):
+        B200WhisperModel("small.en", local_files_only=True, download_root=str(tmp_path))
+    m = _oracle_model()
+    with pytest.raises(FileNotFoundError, match="tokenizer.json"):
+        B200WhisperModel("micro.en", engine=m.model, feature_extractor=m.feature_extractor)
+    ok = B200WhisperModel("micro.en", engine=m.model, feature_extractor=m.feature_extractor, hf_tokenizer="synthetic")
+    assert ok.hf_tokenizer.get_vocab_size() >= m.model.vocab_size - 1
+
+
 def _oracle_model(name="micro.en", seed=0):
     from oracle.engine import OracleWhisper
     from oracle.mel import OracleFeatureExtractor

@@ -114,29 +114,40 @@ class B200Whisper:
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_model(cls, model_size_or_path: str, device_index=0, compute_type="float16", weights=None, seed: int = 0,
-                   max_streams: int = 8, max_beam: int = 5, **kw) -> "B200Whisper":
-        """Size name -> architecture; weights from ``weights`` (dict), a model directory -- HF ``model.safetensors``
-        or the CTranslate2 ``model.bin`` the reference's download_model fetches -- or, because no checkpoint exists
-        offline, seeded random initialisation of that architecture."""
+                   max_streams: int = 8, max_beam: int = 5, download_root: Optional[str] = None,
+                   local_files_only: bool = False, **kw) -> "B200Whisper":
+        """Resolve ``model_size_or_path`` the way the reference does (faster_whisper_backend.py:133-178,
+        transcriber_faster_whisper.py:620-656): a local directory holding HF ``model.safetensors`` or the
+        CTranslate2 ``model.bin``; else a size name / hub id looked up through ``huggingface_hub``
+        (``Systran/faster-whisper-<size>``, honouring ``download_root`` / ``local_files_only``).  When no
+        checkpoint can be found this RAISES -- a transcriber serving random weights is never built silently.
+        ``weights`` may be a tensor dict, or the explicit opt-in ``"random"`` (seeded random initialisation of
+        the named architecture: bench.py and the tests, which run without network or checkpoints)."""
         import os
         from . import weights as W
-        if weights is None and isinstance(model_size_or_path, str) and os.path.isdir(model_size_or_path):
-            weights = W.load_model_dir(model_size_or_path)
-            if "alignment_heads" not in kw or kw["alignment_heads"] is None:
+        if isinstance(weights, str):
+            if weights != "random":
+                raise ValueError(f"weights={weights!r}: pass a tensor dict, None, or the explicit opt-in 'random'")
+            dims = dims_for(model_size_or_path)
+            return cls(dims, W.random_init(dims, seed=seed), device_index=device_index, compute_type=compute_type,
+                       max_streams=max_streams, max_beam=max_beam, **kw)
+        model_dir = None
+        if weights is None:
+            model_dir = W.resolve_model_dir(model_size_or_path, download_root=download_root, local_files_only=local_files_only)
+            weights = W.load_model_dir(model_dir)
+            if kw.get("alignment_heads") is None:
                 from .ct2_format import read_ct2_config
-                heads = read_ct2_config(model_size_or_path).get("alignment_heads")
+                heads = read_ct2_config(model_dir).get("alignment_heads")
                 if heads:
                     kw["alignment_heads"] = heads
-        if weights is not None:
-            try:
-                dims = dims_for(model_size_or_path)
-            except KeyError:
-                dims = W.infer_dims(weights, str(model_size_or_path))
-        else:
+        try:
             dims = dims_for(model_size_or_path)
-            weights = W.random_init(dims, seed=seed)
-        return cls(dims, weights, device_index=device_index, compute_type=compute_type, max_streams=max_streams,
-                   max_beam=max_beam, **kw)
+        except KeyError:
+            dims = W.infer_dims(weights, str(model_size_or_path))
+        eng = cls(dims, weights, device_index=device_index, compute_type=compute_type, max_streams=max_streams,
+                  max_beam=max_beam, **kw)
+        eng.model_dir = model_dir
+        return eng
 
     def _load_weights(self, weights) -> None:
         from .feature_extractor import mel_filters

@@ -446,20 +446,29 @@ class B200WhisperModel:
                  max_streams: int = 8, max_beam: int = 5, vad=None, **model_kwargs):
         """``engine`` / ``hf_tokenizer`` / ``feature_extractor`` injection is for tests; the
         product path builds the CUDA engine (whisperlive_b200.engine.B200Whisper) and fails
-        loudly when libwlb200.so or a GPU is missing."""
+        loudly when libwlb200.so, a GPU, the checkpoint or tokenizer.json is missing.
+        ``weights="random"`` / ``hf_tokenizer="synthetic"`` are the explicit opt-ins bench.py and
+        the tests use (no checkpoints offline)."""
         self.logger = logger
         self._vad = vad
         if engine is None:
             from .engine import B200Whisper  # raises if the CUDA library cannot be loaded
             engine = B200Whisper.from_model(model_size_or_path, device_index=device_index, compute_type=compute_type,
-                                            weights=weights, seed=seed, max_streams=max_streams, max_beam=max_beam)
+                                            weights=weights, seed=seed, max_streams=max_streams, max_beam=max_beam,
+                                            download_root=download_root, local_files_only=local_files_only)
         self.model = engine
+        model_dir = getattr(engine, "model_dir", None) or model_size_or_path
+        if isinstance(hf_tokenizer, str):
+            if hf_tokenizer != "synthetic":
+                raise ValueError("hf_tokenizer must be a tokenizers.Tokenizer, None, or the explicit opt-in 'synthetic'")
+            from .tokenizer import build_synthetic_tokenizer
+            hf_tokenizer = build_synthetic_tokenizer(engine.vocab_size)
         if hf_tokenizer is None:
-            hf_tokenizer = self._load_tokenizer(model_size_or_path, files)
+            hf_tokenizer = self._load_tokenizer(model_dir, files)
         self.hf_tokenizer = hf_tokenizer
         if feature_extractor is None:
             from .feature_extractor import FeatureExtractor
-            feature_extractor = FeatureExtractor(engine=engine, **self._get_feature_kwargs(model_size_or_path, files))
+            feature_extractor = FeatureExtractor(engine=engine, **self._get_feature_kwargs(model_dir, files))
         self.feature_extractor = feature_extractor
         self.input_stride = 2
         self.num_samples_per_token = self.feature_extractor.hop_length * self.input_stride
@@ -476,9 +485,11 @@ class B200WhisperModel:
         cand = os.path.join(path, "tokenizer.json") if isinstance(path, str) else None
         if cand and os.path.isfile(cand):
             return tokenizers.Tokenizer.from_file(cand)
-        from .tokenizer import build_synthetic_tokenizer
-        self.logger.warning("no tokenizer.json for %s: using the synthetic vocabulary (offline build)", path)
-        return build_synthetic_tokenizer(self.model.vocab_size)
+        # reference :620-656 resolves tokenizer.json from the model directory or the hub; there is no fallback
+        # vocabulary (a transcriber that emits made-up text must never start silently)
+        raise FileNotFoundError(
+            f"tokenizer.json not found for {path!r}: pass a model directory that holds it, files={{'tokenizer.json': ...}}, "
+            "or hf_tokenizer='synthetic' (fabricated vocabulary, bench/tests only)")
 
     def _get_feature_kwargs(self, path: str, files: Optional[dict]) -> dict:
         cfg: dict = {}

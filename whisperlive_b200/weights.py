@@ -124,6 +124,33 @@ def load_model_dir(path: str) -> Dict[str, torch.Tensor]:
     raise FileNotFoundError(f"{path}: neither model.safetensors nor model.bin")
 
 
+def resolve_model_dir(model_size_or_path: str, download_root=None, local_files_only: bool = False) -> str:
+    """Directory holding the checkpoint + tokenizer.json for a path, a size name or a hub id.
+    Mirrors the reference's resolution order (faster_whisper_backend.py:133-178): local directory first,
+    then the hub snapshot of ``Systran/faster-whisper-<size>`` (CT2 format, what ``download_model`` fetches).
+    Raises FileNotFoundError with the reason instead of falling back to anything."""
+    if isinstance(model_size_or_path, str) and os.path.isdir(model_size_or_path):
+        return model_size_or_path
+    name = str(model_size_or_path)
+    repo = name if "/" in name else f"Systran/faster-whisper-{name}"
+    try:
+        import huggingface_hub
+    except Exception as e:
+        raise FileNotFoundError(f"{name!r} is not a model directory and huggingface_hub is not importable ({e})") from e
+    allow = ["config.json", "preprocessor_config.json", "model.bin", "model.safetensors", "tokenizer.json", "vocabulary.*"]
+    try:
+        return huggingface_hub.snapshot_download(repo, cache_dir=download_root, local_files_only=local_files_only,
+                                                 allow_patterns=allow)
+    except Exception as first:
+        try:   # offline / no network: a previously downloaded snapshot still resolves
+            return huggingface_hub.snapshot_download(repo, cache_dir=download_root, local_files_only=True, allow_patterns=allow)
+        except Exception:
+            raise FileNotFoundError(
+                f"no checkpoint for {name!r}: not a local directory and the hub snapshot {repo!r} is unavailable "
+                f"({type(first).__name__}: {first}).  Pass a model directory (model.safetensors or model.bin + "
+                f"tokenizer.json), or weights='random' for a seeded random-init engine (bench/tests only).") from first
+
+
 def infer_dims(weights: Dict[str, torch.Tensor], name: str = "custom") -> WhisperDims:
     d = weights["model.encoder.conv1.weight"].shape[0]
     n_mels = weights["model.encoder.conv1.weight"].shape[1]
