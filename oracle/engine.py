@@ -116,7 +116,7 @@ class OracleWhisper:
                  length_penalty=1, repetition_penalty=1, no_repeat_ngram_size=0, max_length=448,
                  return_scores=False, return_no_speech_prob=False, max_initial_timestamp_index=50,
                  suppress_blank=True, suppress_tokens=(-1,), sampling_topk=1, sampling_temperature=1,
-                 seed: int = 0, max_length_per_stream=None) -> List[GenerationResult]:
+                 seed: int = 0, max_length_per_stream=None, trace: bool = False) -> List[GenerationResult]:
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size: the reference passes 1 / 0")
         eo = self._as_encoded(features)
@@ -128,9 +128,11 @@ class OracleWhisper:
                               max_length=max_length if max_length_per_stream is None else max_length_per_stream[b],
                               suppress_blank=suppress_blank,
                               suppress_tokens=sup, max_initial_timestamp_index=max_initial_timestamp_index,
-                              sampling_topk=sampling_topk, sampling_temperature=sampling_temperature, seed=seed)
+                              sampling_topk=sampling_topk, sampling_temperature=sampling_temperature, seed=seed, trace=trace)
             r: StreamResult = search_stream(self._stream_step_fn(eo, b), list(prompt), self.spec, opts, stream_index=b)
-            out.append(GenerationResult(r.sequences_ids, r.scores, r.no_speech_prob, r.steps, r.margins))
+            g = GenerationResult(r.sequences_ids, r.scores, r.no_speech_prob, r.steps, r.margins)
+            g.trace, g.row_margins, g.row_tokens = r.trace, r.row_margins, r.row_tokens
+            out.append(g)
         return out
 
     # -- ctranslate2.models.Whisper.detect_language ----------------------------------------

@@ -86,6 +86,7 @@ class GenOptions:
     sampling_topk: int = 1
     sampling_temperature: float = 1.0
     seed: int = 0
+    trace: bool = False
 
 
 def max_new_tokens(prompt_len: int, max_length: int) -> int:
@@ -113,16 +114,32 @@ def gumbel_noise(seed: int, row: int, step: int, vocab: int) -> np.ndarray:
     return (-np.log(-np.log(u))).astype(np.float32)
 
 
+def sample_begin(prompt: Sequence[int], spec: VocabSpec) -> int:
+    """CT2's prompt length [upstream-recalled, models/whisper.cc]: index after <|startoftranscript|> and every
+    following id in [sot, no_timestamps] (language, task, notimestamps).  Prompt tokens from there on -- the
+    ``prefix`` built at transcriber_faster_whisper.py:1505-1511, including its leading <|0.00|> -- are treated as
+    already-sampled text by the timestamp rules."""
+    if spec.sot not in prompt:
+        return len(prompt)
+    i = list(prompt).index(spec.sot) + 1
+    while i < len(prompt) and spec.sot <= prompt[i] <= spec.no_timestamps:
+        i += 1
+    return i
+
+
 def apply_processors(logits: torch.Tensor, gen: List[int], spec: VocabSpec, opts: GenOptions,
-                     use_timestamps: bool) -> torch.Tensor:
-    """One row: raw logits [V] f32 -> log-probabilities [V] f32 after all masks."""
+                     use_timestamps: bool, prefix: Sequence[int] = ()) -> torch.Tensor:
+    """One row: raw logits [V] f32 -> log-probabilities [V] f32 after all masks.  ``gen`` are the generated tokens,
+    ``prefix`` the prompt tokens after the sot sequence (history of the timestamp rules = prefix + gen; blank
+    suppression is keyed to the first generated step)."""
     x = logits.clone()
     if len(opts.suppress_tokens):
         x[torch.as_tensor(list(opts.suppress_tokens), dtype=torch.long)] = NEG_INF
-    first = len(gen) == 0
-    if opts.suppress_blank and first:
+    if opts.suppress_blank and len(gen) == 0:
         x[spec.blank] = NEG_INF
         x[spec.eot] = NEG_INF
+    gen = list(prefix) + list(gen)
+    first = len(gen) == 0
     tb = spec.timestamp_begin
     if use_timestamps:
         x[spec.no_timestamps] = NEG_INF
@@ -176,6 +193,12 @@ class StreamResult:
     steps: int = 0
     # per-step decision margins (top1 - top2 of the ranked candidates) for divergence-aware comparison
     margins: List[float] = field(default_factory=list)
+    # beam search only, when GenOptions.trace: per step {"alive": [token tuples], "cand": [(beam, token, total)]}
+    # with 2K+2 ranked candidates -- lets a test name the near-tie behind a pruning difference
+    trace: List[dict] = field(default_factory=list)
+    # sampling only: per hypothesis row, the margin of the Gumbel-perturbed arg-max at every step
+    row_margins: dict = field(default_factory=dict)
+    row_tokens: List[List[int]] = field(default_factory=list)
 
 
 def _normalise(cum: float, n_tokens: int, length_penalty: float) -> float:
@@ -190,7 +213,9 @@ def search_stream(step_fn, prompt: List[int], spec: VocabSpec, opts: GenOptions,
     ``step_fn(tokens [R,T] int64, parents or None) -> logits [R,T,V]`` advances the
     decoder: ``parents`` (LongTensor [R]) re-gathers cache rows first (None keeps them)."""
     res = StreamResult()
-    use_ts = not (len(prompt) > 0 and prompt[-1] == spec.no_timestamps)
+    sb = sample_begin(prompt, spec)
+    prefix = list(prompt[sb:])
+    use_ts = not (sb > 0 and prompt[sb - 1] == spec.no_timestamps)
     sot_index = prompt.index(spec.sot) if spec.sot in prompt else None
     n_new = max_new_tokens(len(prompt), opts.max_length)
 
@@ -225,14 +250,18 @@ def search_stream(step_fn, prompt: List[int], spec: VocabSpec, opts: GenOptions,
                 if done[r]:
                     nxt.append(spec.eot)
                     continue
-                logp = apply_processors(logits[r], gens[r], spec, opts, use_ts)
+                logp = apply_processors(logits[r], gens[r], spec, opts, use_ts, prefix)
                 if sampling:
                     z = logp / opts.sampling_temperature
                     if opts.sampling_topk > 0:
                         kth = torch.topk(z, opts.sampling_topk).values[-1]
                         z = torch.where(z >= kth, z, torch.full_like(z, NEG_INF))
                     z = z + torch.from_numpy(gumbel_noise(opts.seed, stream_index * 64 + r, step, spec.vocab))
-                    tok = int(torch.argmax(z))
+                    zv, zi = topk_stable(z, 2)
+                    tok = int(zi[0])
+                    res.row_margins.setdefault(r, []).append(float(zv[0] - zv[1]))
+                    if r == 0:
+                        res.margins.append(float(zv[0] - zv[1]))
                 else:
                     vals, idx = topk_stable(logp, 2)
                     tok = int(idx[0])
@@ -251,6 +280,7 @@ def search_stream(step_fn, prompt: List[int], spec: VocabSpec, opts: GenOptions,
                 break
             cur = torch.tensor(nxt, dtype=torch.long)[:, None]
         hyps = [Hypothesis(g, c, _normalise(c, len(g), opts.length_penalty)) for g, c in zip(gens, cums)]
+        res.row_tokens = [list(g) for g in gens]
     else:
         K = opts.beam_size
         max_cand = int(round(K * opts.patience))
@@ -264,8 +294,12 @@ def search_stream(step_fn, prompt: List[int], spec: VocabSpec, opts: GenOptions,
             if step == 0 and sot_index == len(prompt) - 1:
                 res.no_speech_prob = float(torch.softmax(logits[0], -1)[spec.no_speech])
             n_alive = len(alive_tokens)
-            total = torch.stack([apply_processors(logits[r], alive_tokens[r], spec, opts, use_ts) + alive_cum[r]
+            total = torch.stack([apply_processors(logits[r], alive_tokens[r], spec, opts, use_ts, prefix) + alive_cum[r]
                                  for r in range(n_alive)]).reshape(-1)
+            if opts.trace:
+                tv, ti = topk_stable(total, 2 * K + 2)
+                res.trace.append({"alive": [tuple(t) for t in alive_tokens],
+                                  "cand": [(int(i) // spec.vocab, int(i) % spec.vocab, float(v)) for v, i in zip(tv, ti)]})
             vals, idx = topk_stable(total, 2 * K)
             n_c = idx.shape[0]
             if n_c >= 2:

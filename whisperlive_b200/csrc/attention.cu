@@ -43,7 +43,9 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
     kv = __ldg(reinterpret_cast<const float2*>(qkv.bias + d + c0));
     vv = __ldg(reinterpret_cast<const float2*>(qkv.bias + 2 * d + c0));
   }
+  tl_stamp(TL_SELF, 0);
   pdl_wait();
+  tl_stamp(TL_SELF, 1);
   {
     const float* row = qkv.ptr + (long)r * 3 * d + c0;
 #pragma unroll 4
@@ -248,7 +250,9 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     return;
   }
   // -------------------------------------------------------------------- consumer warps (128 threads)
+  tl_stamp(TL_CROSS, 0);
   pdl_wait();   // q comes from the projection GEMM right before this kernel
+  tl_stamp(TL_CROSS, 1);
   const int g = lane >> 2, tq = lane & 3;    // mma fragment coordinates: group (row / n index), thread-in-group
   int stage = 0;
   uint32_t phase = 0;
@@ -479,7 +483,9 @@ __global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict
   const int b = r / rows_per_stream, j = r % rows_per_stream;
   pdl_trigger();
   if (s.done[b]) return;
+  tl_stamp(TL_COMBINE, 0);
   pdl_wait();
+  tl_stamp(TL_COMBINE, 1);
   const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
   float M = -INFINITY;
   for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(p + (long)sp * MAX_ROWS_PER_STREAM * 66));
@@ -586,6 +592,7 @@ static void prime_cross() {
   WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<NQ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   WL_CUDA(cudaFuncSetAttribute(cross_attn_kernel<NQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
+void attention_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
 void attention_prime() {
   prime_cross<1>();
   prime_cross<2>();

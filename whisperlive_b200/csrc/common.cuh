@@ -73,6 +73,29 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   WL_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
+// ----------------------------------------------------------------------------------- in-graph timeline (debug)
+// WLB200_TIMELINE=<file>: every decode-step kernel stamps %globaltimer at entry (what=0) and right after its
+// dependency wait (what=1) from one thread of block 0 into a device log (slot 0 = entry counter).  The deltas between
+// consecutive "ready" stamps are the per-kernel cost INSIDE the replayed CUDA graph, which ncu cannot show
+// (tools/timeline.py).  One pointer per translation unit (no relocatable device code), bound by tl_bind().
+constexpr unsigned TL_CAP = 1u << 20;
+static __device__ unsigned long long* wl_tl_buf = nullptr;
+__device__ __forceinline__ void tl_stamp_any(int kernel_id, int what) {
+  unsigned long long* buf = wl_tl_buf;
+  if (buf != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned idx = atomicAdd(reinterpret_cast<unsigned*>(buf), 1u);
+    if (idx < TL_CAP) buf[1 + idx] = (t << 8) | ((unsigned long long)kernel_id << 2) | (unsigned long long)what;
+  }
+}
+__device__ __forceinline__ void tl_stamp(int kernel_id, int what) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tl_stamp_any(kernel_id, what);
+}
+static inline void tl_bind_tu(unsigned long long* p) { cudaMemcpyToSymbol(wl_tl_buf, &p, sizeof(p)); }
+enum TlKernel : int { TL_EMBED = 1, TL_LN = 2, TL_GEMM_PART = 3, TL_SELF = 4, TL_CROSS = 5, TL_COMBINE = 6, TL_GELU = 7,
+                      TL_SROWS = 8, TL_SSTREAMS = 9, TL_GEMM = 10, TL_DSTEP = 11 };
+
 // ----------------------------------------------------------------------------------- generic
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

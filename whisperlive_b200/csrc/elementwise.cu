@@ -5,6 +5,8 @@
 
 namespace wl {
 
+void elementwise_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
+
 // ---------------------------------------------------------------------------- prep_features
 // [B][n_mels][3000] f32 -> [B][3002][n_mels] fp16 with one zero row before and after (conv k=3, pad=1
 // becomes a plain strided GEMM over overlapping rows).  32x32 smem transpose tiles.
@@ -106,7 +108,9 @@ __global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict
     const int c = i * 128 + tid;
     v[i] = (c < n4 && upd.nsplit > 0 && upd.bias) ? __ldg(reinterpret_cast<const float4*>(upd.bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  tl_stamp(TL_LN, 0);
   pdl_wait();
+  tl_stamp(TL_LN, 1);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = i * 128 + tid;
@@ -197,7 +201,9 @@ __global__ void gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int ro
   const int c = (int)(i4 % c4n);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (in.bias) v = __ldg(reinterpret_cast<const float4*>(in.bias) + c);
+  tl_stamp(TL_GELU, 0);
   pdl_wait();
+  tl_stamp(TL_GELU, 1);
   const float4* p4 = reinterpret_cast<const float4*>(in.ptr) + i4;
   const long st4 = in.stride >> 2;
 #pragma unroll 4
@@ -261,6 +267,7 @@ __global__ void decoder_embed_kernel(DecodeState s, const __half* __restrict__ e
   const int r = blockIdx.x;
   pdl_trigger();
   pdl_wait();
+  tl_stamp(TL_EMBED, 1);
   if (!s.active[r]) return;
   const int tok = s.tok_in[r], pos = s.pos[r];
   for (int c = threadIdx.x; c < d; c += blockDim.x)

@@ -21,6 +21,10 @@ void search_prime();
 void flash_attn_prime();
 void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt, __half* out, int nb, int H, int d);
 long other_launch_count();
+void gemm_tl_bind(unsigned long long* p);
+void attention_tl_bind(unsigned long long* p);
+void elementwise_tl_bind(unsigned long long* p);
+void search_tl_bind(unsigned long long* p);
 }  // namespace wl
 
 static std::string g_init_error;
@@ -103,6 +107,9 @@ struct wl_ctx {
   float* h_flt = nullptr;
   size_t h_int_cap = 0, h_flt_cap = 0;
   std::map<std::string, GraphEntry> graphs;
+  // WLB200_TIMELINE: in-graph per-kernel timestamps (common.cuh), dumped after every wl_generate
+  unsigned long long* tl_dev = nullptr;
+  std::string tl_path;
 };
 
 #define API_BEGIN(ctx)                                          \
@@ -182,6 +189,13 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     attention_prime();
     search_prime();
     flash_attn_prime();
+    if (const char* tl = getenv("WLB200_TIMELINE")) {
+      c->tl_path = tl;
+      WL_CUDA(cudaMalloc((void**)&c->tl_dev, (size_t)(TL_CAP + 1) * 8));
+      WL_CUDA(cudaMemset(c->tl_dev, 0, (size_t)(TL_CAP + 1) * 8));
+      c->allocs.push_back(c->tl_dev);
+      gemm_tl_bind(c->tl_dev); attention_tl_bind(c->tl_dev); elementwise_tl_bind(c->tl_dev); search_tl_bind(c->tl_dev);
+    }
     c->enc.resize(c->Le);
     c->dec.resize(c->Ld);
     for (int i = c->NS - 1; i >= 0; --i) c->slot_free.push_back(i);
@@ -451,6 +465,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
   s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
   s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
+  s.pre_n = dalloc<int>(c, B); s.pre_last = dalloc<int>(c, B); s.pre_penult = dalloc<int>(c, B); s.pre_lts = dalloc<int>(c, B);
   WL_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
   API_END(c)
@@ -780,9 +795,9 @@ static VocabIds vocab_ids(wl_ctx* c) {
 // upload prompts & per-stream metadata; returns max steps
 static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t* prompts, const int32_t* off, int max_length,
                           bool forced, const int32_t* max_len_ps = nullptr) {
-  ensure_host(c, (size_t)B * (T_MAX + 8), 16);
+  ensure_host(c, (size_t)B * (T_MAX + 16), 16);
   int* hp = c->h_int;                      // [B][T_MAX]
-  int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len  (6 x B)
+  int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len, pre_n, pre_last, pre_penult, pre_lts
   int max_steps = 0;
   for (int b = 0; b < B; ++b) {
     const int P = off[b + 1] - off[b];
@@ -805,12 +820,27 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
     } else {
       max_steps = std::max(max_steps, P);
     }
+    // end of the sot sequence = CT2's prompt length: sot, then every following id in [sot, no_timestamps]
+    // (language, task, notimestamps); the tokens after it are a prefix that counts as sampled text
+    int sb = P;
+    if (sot >= 0) {
+      sb = sot + 1;
+      while (sb < P && prompts[off[b] + sb] >= c->cfg.sot && prompts[off[b] + sb] <= c->cfg.no_timestamps) ++sb;
+    }
+    const int npre = P - sb;
+    int lts = -1;
+    for (int i = sb; i < P; ++i)
+      if (prompts[off[b] + i] >= c->cfg.timestamp_begin) lts = prompts[off[b] + i];
     meta[0 * B + b] = slots[b];
     meta[1 * B + b] = P;
     meta[2 * B + b] = sot;
-    meta[3 * B + b] = prompts[off[b] + P - 1] != c->cfg.no_timestamps;
+    meta[3 * B + b] = sb >= 1 ? prompts[off[b] + sb - 1] != c->cfg.no_timestamps : 1;
     meta[4 * B + b] = n_new;
     meta[5 * B + b] = forced ? P : 0;
+    meta[6 * B + b] = forced ? 0 : npre;
+    meta[7 * B + b] = npre >= 1 ? prompts[off[b] + P - 1] : -1;
+    meta[8 * B + b] = npre >= 2 ? prompts[off[b] + P - 2] : -1;
+    meta[9 * B + b] = forced ? -1 : lts;
   }
   const DecodeState& s = c->ds;
   cudaStream_t st = c->st;
@@ -821,6 +851,10 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
   WL_CUDA(cudaMemcpyAsync(s.use_ts, meta + 3 * B, B * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaMemcpyAsync(s.n_new, meta + 4 * B, B * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaMemcpyAsync(s.force_len, meta + 5 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.pre_n, meta + 6 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.pre_last, meta + 7 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.pre_penult, meta + 8 * B, B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.pre_lts, meta + 9 * B, B * 4, cudaMemcpyHostToDevice, st));
   return max_steps;
 }
 
@@ -886,7 +920,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     exec = ge.exec;
     graph_kernels = ge.kernels;
   }
-  ensure_host(c, (size_t)B * (T_MAX + 8) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
+  ensure_host(c, (size_t)B * (T_MAX + 16) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
   int* h_done = c->h_int;  // reuse (prompts are already on the device: the copies above are stream-ordered)
   WL_CUDA(cudaStreamSynchronize(st));
   int ran = 0;
@@ -923,6 +957,13 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   WL_CUDA(cudaMemcpyAsync(h_ns, s.no_speech, B * 4, cudaMemcpyDeviceToHost, st));
   WL_CUDA(cudaStreamSynchronize(st));
   WL_CUDA(cudaEventElapsedTime(&c->last_ms[2], c->ev0, c->ev1));
+  if (c->tl_dev) {   // dump + reset the in-graph timeline of this call
+    std::vector<unsigned long long> h(TL_CAP + 1);
+    WL_CUDA(cudaMemcpy(h.data(), c->tl_dev, h.size() * 8, cudaMemcpyDeviceToHost));
+    const size_t n = std::min<size_t>((size_t)(h[0] & 0xffffffffu), TL_CAP);
+    if (FILE* f = fopen(c->tl_path.c_str(), "wb")) { fwrite(h.data() + 1, 8, n, f); fclose(f); }
+    WL_CUDA(cudaMemset(c->tl_dev, 0, 8));
+  }
   const int NH = o->num_hypotheses;
   for (int b = 0; b < B; ++b) {
     const int cnt = std::min(h_cnt[b], MAX_HYPS);

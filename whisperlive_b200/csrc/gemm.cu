@@ -369,7 +369,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sA + kb * A_STAGE_BYTES, &tmA, &full[kb], (kb0 + kb) * BK, ca1, ca2, ca3);
             }
           }
+          if (blockIdx.x == 0) tl_stamp_any(KIND == EPI_PART ? TL_GEMM_PART : TL_GEMM, 0);
           pdl_wait();
+          if (blockIdx.x == 0) tl_stamp_any(KIND == EPI_PART ? TL_GEMM_PART : TL_GEMM, 1);
           first = false;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -597,6 +599,7 @@ static void prime_kind() {
   prime_cfg<128, 5, 1, KIND>();
   prime_cfg<256, 4, 1, KIND>();
 }
+void gemm_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
 void gemm_prime() {
   prime_kind<EPI_ROW>();
   prime_kind<EPI_COL>();

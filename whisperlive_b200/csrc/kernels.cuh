@@ -68,6 +68,10 @@ struct DecodeState {
   int* fed;          // [B] index of the prompt token fed at the current step
   int* sot_index;    // [B] or -1
   int* use_ts;       // [B]
+  int* pre_n;        // [B] prompt tokens after the sot sequence (a ``prefix``): CT2 treats them as already-sampled text
+  int* pre_last;     // [B] last / second-to-last of those tokens (-1 when absent) and the last timestamp among them:
+  int* pre_penult;   // [B]   seeds of the timestamp rules' history
+  int* pre_lts;      // [B]
   int* n_new;        // [B] max new tokens
   int* step;         // [B] generation steps done
   int* done;         // [B]

@@ -15,7 +15,7 @@ struct MaskCtx {
 
 // the rule-based part of the logits processors (everything but the user's suppress list)
 __device__ __forceinline__ bool rule_masked(int t, const MaskCtx& c) {
-  if (c.first && c.suppress_blank && (t == c.blank || t == c.eot)) return true;
+  if (c.suppress_blank && (t == c.blank || t == c.eot)) return true;
   if (c.use_ts) {
     if (t == c.no_timestamps) return true;
     if (c.first) {
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   const int r = blockIdx.x, tid = threadIdx.x;
   const int b = r / o.rows_per_stream;
   pdl_trigger();
+  tl_stamp(TL_SROWS, 0);
   if (!s.active[r] || s.done[b]) return;   // per-step state, complete before this step started
   __shared__ float red[2 * SR_WARPS];
   __shared__ float wkey[SR_WARPS];
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   const float* lg = logits + (long)r * v.vocab_ld;
   const int fed = s.fed[b], P = s.prompt_len[b];
   pdl_wait();   // logits come from the vocabulary GEMM right before this kernel
+  tl_stamp(TL_SROWS, 1);
   if (fed == s.sot_index[b] && r == b * o.rows_per_stream) {
     float m = -INFINITY, sm = 0.f;
     for (int t = tid; t < v.vocab; t += SR_THREADS) lse_merge(m, sm, lg[t], 1.f);
@@ -126,16 +128,21 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
 
   const int glen = s.gen_len[r];
   const int* hist = s.hist + (long)r * T_MAX;
+  // CTranslate2 ends the "prompt" at the sot sequence (sot, language, task, notimestamps): whatever follows -- the
+  // ``prefix`` of transcriber_faster_whisper.py:1505-1511, incl. its leading <|0.00|> -- counts as sampled text for the
+  // timestamp rules.  Blank suppression is keyed to the first GENERATED step.
+  const int npre = s.pre_n[b], nhist = glen + npre;
   MaskCtx c;
   c.suppress = o.suppress_mask;
-  c.first = glen == 0;
-  c.suppress_blank = o.suppress_blank;
+  c.first = nhist == 0;
+  c.suppress_blank = o.suppress_blank && glen == 0;
   c.use_ts = s.use_ts[b];
   c.max_initial = o.max_initial_ts;
   c.eot = v.eot; c.no_timestamps = v.no_timestamps; c.ts_begin = v.ts_begin; c.blank = v.blank;
-  const int last = glen > 0 ? hist[glen - 1] : -1;
-  c.last_is_ts = glen > 0 && last >= v.ts_begin;
-  c.penult_is_ts = glen < 2 || hist[glen - 2] >= v.ts_begin;
+  const int last = glen > 0 ? hist[glen - 1] : s.pre_last[b];
+  const int penult = glen > 1 ? hist[glen - 2] : (glen == 1 ? s.pre_last[b] : s.pre_penult[b]);
+  c.last_is_ts = nhist > 0 && last >= v.ts_begin;
+  c.penult_is_ts = nhist < 2 || penult >= v.ts_begin;
   const int lts = s.last_ts[r];
   c.has_ts = lts >= 0;
   c.ts_cutoff = (c.last_is_ts && !c.penult_is_ts) ? lts : lts + 1;
@@ -264,6 +271,7 @@ void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, con
   note_launch(1);
 }
 
+void search_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
 void search_prime() {
   WL_CUDA(cudaFuncSetAttribute(search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
 }
@@ -278,7 +286,9 @@ __device__ void finish_stream(DecodeState& s, int b, int Kr) {
 __global__ void __launch_bounds__(128) search_streams_kernel(DecodeState s, SearchOpts o, VocabIds v) {
   const int b = blockIdx.x, tid = threadIdx.x;
   pdl_trigger();
+  tl_stamp(TL_SSTREAMS, 0);
   pdl_wait();
+  tl_stamp(TL_SSTREAMS, 1);
   if (s.done[b]) return;
   const int Kr = o.rows_per_stream, row0 = b * Kr;
   const int P = s.prompt_len[b], fed = s.fed[b];
@@ -495,7 +505,7 @@ __global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v) {
     s.active[r] = on ? 1 : 0;
     s.cum[r] = 0.f;
     s.gen_len[r] = 0;
-    s.last_ts[r] = -1;
+    s.last_ts[r] = s.pre_lts[b];
     s.row_done[r] = 0;
     s.nospeech_row[r] = 0.f;
   }
