@@ -116,9 +116,13 @@ class OracleWhisper:
                  length_penalty=1, repetition_penalty=1, no_repeat_ngram_size=0, max_length=448,
                  return_scores=False, return_no_speech_prob=False, max_initial_timestamp_index=50,
                  suppress_blank=True, suppress_tokens=(-1,), sampling_topk=1, sampling_temperature=1,
-                 seed: int = 0, max_length_per_stream=None, trace: bool = False) -> List[GenerationResult]:
+                 seed=None, max_length_per_stream=None, trace: bool = False) -> List[GenerationResult]:
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size: the reference passes 1 / 0")
+        if seed is None:   # same rule as whisperlive_b200.engine.B200Whisper.generate: a per-engine sampling-call counter
+            if int(beam_size) == 1 and sampling_topk != 1 and sampling_temperature > 0:
+                self._sampling_calls = getattr(self, "_sampling_calls", 0) + 1
+            seed = getattr(self, "_sampling_calls", 0)
         eo = self._as_encoded(features)
         sup = [t for t in (suppress_tokens or ()) if t >= 0]
         out = []

@@ -62,8 +62,10 @@ def main():
         theirs = G.reference_model(ref_tr, engine, dims)     # the reference's own WhisperModel over the same engine
         audios = [synth.speech_like(6.0, seed=1), synth.speech_like(3.0, seed=2), synth.speech_like(9.5, seed=3)]
         lang = None if dims.multilingual else "en"
-        out[model_name] = dict(over_b200_model=run_batcher(ref_bi, mine, audios, lang),
-                               over_reference_model=run_batcher(ref_bi, theirs, audios, lang))
+        a = run_batcher(ref_bi, mine, audios, lang)
+        engine._sampling_calls = 0     # both runs start from the same sampling-noise state (CT2: a fresh generator)
+        b = run_batcher(ref_bi, theirs, audios, lang)
+        out[model_name] = dict(over_b200_model=a, over_reference_model=b)
     print(json.dumps(out))
 
 

@@ -7,6 +7,22 @@ namespace wl {
 
 void elementwise_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
 
+// ---------------------------------------------------------------------------- cast_weight_f16
+__global__ void cast_weight_kernel(const float* __restrict__ in, __half* __restrict__ out, long n, long b, long k) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    // output index i = (a, kk, bb); input index = (a, bb, kk)
+    const long bb = i % b, kk = (i / b) % k, a = i / (b * k);
+    out[i] = __float2half_rn(in[(a * b + bb) * k + kk]);
+  }
+}
+void cast_weight_f16(cudaStream_t st, const float* in, __half* out, long a, long b, long k) {
+  const long n = a * b * k;
+  const int grid = (int)std::min<long>((n + 255) / 256, 148L * 16);
+  cast_weight_kernel<<<grid, 256, 0, st>>>(in, out, n, b, k);
+  WL_CUDA(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------- prep_features
 // [B][n_mels][3000] f32 -> [B][3002][n_mels] fp16 with one zero row before and after (conv k=3, pad=1
 // becomes a plain strided GEMM over overlapping rows).  32x32 smem transpose tiles.

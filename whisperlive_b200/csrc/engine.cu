@@ -110,6 +110,8 @@ struct wl_ctx {
   // WLB200_TIMELINE: in-graph per-kernel timestamps (common.cuh), dumped after every wl_generate
   unsigned long long* tl_dev = nullptr;
   std::string tl_path;
+  float* stage_f32 = nullptr;   // wl_load_tensor staging (freed by wl_finalize_weights)
+  size_t stage_cap = 0;
 };
 
 #define API_BEGIN(ctx)                                          \
@@ -216,6 +218,7 @@ extern "C" void wl_destroy(wl_ctx* c) {
   for (auto& g : c->graphs)
     if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (void* p : c->allocs) cudaFree(p);
+  if (c->stage_f32) cudaFree(c->stage_f32);
   if (c->h_int) cudaFreeHost(c->h_int);
   if (c->h_flt) cudaFreeHost(c->h_flt);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -264,18 +267,20 @@ extern "C" int wl_load_tensor(wl_ctx* c, const char* name, const float* data, co
     WL_CUDA(cudaMemcpy(p, data, n * sizeof(float), cudaMemcpyHostToDevice));
     c->dev[nm] = p;
   } else {
-    std::vector<__half> h(n);
-    if (ndim == 3) {
-      // conv weight [co][ci][k] -> [co][k][ci] so that conv-as-GEMM reads K = (k, ci) contiguously
-      const int64_t co = sh[0], ci = sh[1], kk = sh[2];
-      for (int64_t a = 0; a < co; ++a)
-        for (int64_t b = 0; b < ci; ++b)
-          for (int64_t k = 0; k < kk; ++k) h[(a * kk + k) * ci + b] = __float2half_rn(data[(a * ci + b) * kk + k]);
-    } else {
-      for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(data[i]);
+    // fp32 -> fp16 (and the conv re-layout) on the device: the host only hands over its buffer.  A large-v3 load
+    // is 1.5 G values; converting them on one host thread took longer than everything else in wl_init together.
+    if (n > c->stage_cap) {
+      if (c->stage_f32) cudaFree(c->stage_f32);
+      c->stage_f32 = nullptr;
+      c->stage_cap = 0;
+      WL_CUDA(cudaMalloc((void**)&c->stage_f32, n * sizeof(float)));
+      c->stage_cap = n;
     }
+    WL_CUDA(cudaMemcpyAsync(c->stage_f32, data, n * sizeof(float), cudaMemcpyHostToDevice, c->st));
     __half* p = dalloc<__half>(c, n, false);
-    WL_CUDA(cudaMemcpy(p, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    if (ndim == 3) cast_weight_f16(c->st, c->stage_f32, p, sh[0], sh[1], sh[2]);   // [co][ci][k] -> [co][k][ci]
+    else cast_weight_f16(c->st, c->stage_f32, p, (long)n, 1, 1);
+    WL_CUDA(cudaStreamSynchronize(c->st));
     c->dev[nm] = p;
   }
   c->shape[nm] = sh;
@@ -409,6 +414,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
     L.ln3_b = (float*)need(c, p + "final_layer_norm.bias", {d});
   }
   build_mel_tables(c);
+  if (c->stage_f32) { cudaFree(c->stage_f32); c->stage_f32 = nullptr; c->stage_cap = 0; }
 
   // ---- encoder workspaces (EB streams per pass, AB streams per attention sub-pass)
   const int H = c->H;
@@ -465,6 +471,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
   s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
   s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
+  s.seed = dalloc<unsigned>(c, 1);
   s.pre_n = dalloc<int>(c, B); s.pre_last = dalloc<int>(c, B); s.pre_penult = dalloc<int>(c, B); s.pre_lts = dalloc<int>(c, B);
   WL_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
@@ -890,6 +897,8 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   }
   const int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false, o->max_length_per_stream);
   WL_CUDA(cudaMemcpyAsync(c->suppress_mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
+  const unsigned seed_host = o->seed;
+  WL_CUDA(cudaMemcpyAsync(c->ds.seed, &seed_host, sizeof(unsigned), cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaEventRecord(c->ev0, st));
   decode_init(st, c->ds, so, vi, B, R);
   const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms, Kr);
@@ -898,8 +907,8 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   long graph_kernels = 0;
   if (o->use_cuda_graph) {
     char key[160];
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x/%u", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
-             so.sampling, *(const unsigned*)&so.temperature, so.seed);
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
+             so.sampling, *(const unsigned*)&so.temperature);
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
       cudaGraph_t g;

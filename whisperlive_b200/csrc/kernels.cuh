@@ -34,6 +34,8 @@ struct PartialSrc {
 // ---------------------------------------------------------------------------- elementwise / normalisation
 // features f32 [B][n_mels][3000] -> fp16 [B][3002][n_mels] (rows 0 and 3001 are zero: conv padding)
 void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int n_mels);
+// weight upload: fp32 [a][b][k] -> fp16 [a][k][b] (conv kernels; b = k = 1 is a plain cast)
+void cast_weight_f16(cudaStream_t st, const float* in, __half* out, long a, long b, long k);
 // y = LayerNorm(x) * gamma + beta ; x f32 [rows][d] -> y fp16 [rows][d] (and optionally f32 copy)
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32,
                     long rows, int d);
@@ -83,6 +85,7 @@ struct DecodeState {
   int* hyp_tok;      // [B][MAX_HYPS][T_MAX]
   int* steps_run;    // [B] decoder steps executed for the stream (diagnostics)
   int* n_done;       // [1] number of finished streams
+  unsigned* seed;    // [1] sampling seed of this generate call (device scalar: the captured graph does not depend on it)
   // teacher-forced mode (detect_language / align / logits test hook)
   int* force_len;    // [B] 0 = normal search; >0 = feed prompt only, then stop
   float* force_prob; // [B][T_MAX] P(prompt[i+1] | prompt[..i]) in teacher-forced mode

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(SR_THREADS) search_rows_kernel(DecodeState s, 
   // selection keys in place: log-prob (beam / greedy) or log-prob / T + Gumbel noise (sampling); rule e drops text
   const int NC = o.beam > 1 ? 2 * o.beam : 1;
   uint32_t gkey = 0;
-  if (o.sampling) gkey = hash_u32((o.seed * 0x9E3779B1u) ^ hash_u32((uint32_t)((b * 64 + (r - b * o.rows_per_stream)) * 65537 + s.step[b])));
+  if (o.sampling) gkey = hash_u32((*s.seed * 0x9E3779B1u) ^ hash_u32((uint32_t)((b * 64 + (r - b * o.rows_per_stream)) * 65537 + s.step[b])));
   float bk = -INFINITY;        // this thread's best remaining entry
   int bt = 0x7fffffff;
   for (int i4 = tid; i4 < n4; i4 += SR_THREADS) {

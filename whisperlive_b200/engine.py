@@ -45,6 +45,11 @@ class _SlotRef:
         self.slots = list(slots)
         self._fin = weakref.finalize(self, B200Whisper._release_slots, weakref.ref(engine), list(slots))
 
+    def release(self) -> None:
+        """Give the slots back now (idempotent); every view sharing this owner becomes invalid."""
+        self._fin()
+        self.slots = []
+
 
 class EncoderOutput:
     """Opaque handle playing the role of the ``ctranslate2.StorageView`` returned by encode():
@@ -61,6 +66,12 @@ class EncoderOutput:
 
     def select(self, indices: Sequence[int]) -> "EncoderOutput":
         return EncoderOutput(self._owner, [self.slots[i] for i in indices], self._d)
+
+    def release(self) -> None:
+        """Explicit end of life of the encoder output and ALL its views (the transcriber calls this at the end of
+        every window instead of relying on reference counting)."""
+        self._owner.release()
+        self.slots = []
 
     def __len__(self):
         return len(self.slots)
@@ -84,6 +95,7 @@ class B200Whisper:
         self.compute_type = "float16"
         self.max_streams = max_streams
         self.max_beam = max_beam
+        self.enc_slots = enc_slots if enc_slots is not None else 2 * max_streams
         self.use_cuda_graph = use_cuda_graph
         self._lock = threading.RLock()
         from .weights import _special_ids
@@ -239,6 +251,11 @@ class B200Whisper:
             raise ValueError(f"encode expects [batch, {self.n_mels}, 3000] features, got {f.shape}")
         slots_all: List[int] = []
         with self._lock:
+            free = self.free_slots()
+            if f.shape[0] > free:
+                raise RuntimeError(f"encode: {f.shape[0]} windows requested but only {free} encoder slots are free "
+                                   f"(pool of {self.enc_slots}; release earlier EncoderOutput handles or encode in groups "
+                                   f"of at most max_streams={self.max_streams})")
             for b0 in range(0, f.shape[0], self.max_streams):
                 part = f[b0:b0 + self.max_streams]
                 slots = np.zeros(part.shape[0], dtype=np.int32)
@@ -259,9 +276,16 @@ class B200Whisper:
                  no_repeat_ngram_size: int = 0, max_length: int = 448, return_scores: bool = False,
                  return_no_speech_prob: bool = False, max_initial_timestamp_index: int = 50, suppress_blank: bool = True,
                  suppress_tokens: Optional[Sequence[int]] = (-1,), sampling_topk: int = 1, sampling_temperature: float = 1,
-                 seed: int = 0, max_length_per_stream: Optional[Sequence[int]] = None) -> List[WhisperGenerationResult]:
+                 seed: Optional[int] = None, max_length_per_stream: Optional[Sequence[int]] = None
+                 ) -> List[WhisperGenerationResult]:
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size other than the reference's 1 / 0")
+        if seed is None:
+            # like CT2's generator state, the noise advances from one sampling call to the next: the rungs of the
+            # temperature ladder and successive windows never replay each other's draws
+            if int(beam_size) == 1 and sampling_topk != 1 and sampling_temperature > 0:
+                self._sampling_calls = getattr(self, "_sampling_calls", 0) + 1
+            seed = getattr(self, "_sampling_calls", 0)
         enc = self._as_encoded(features)
         if len(prompts) != len(enc):
             raise ValueError(f"{len(prompts)} prompts for {len(enc)} encoded streams")

@@ -673,16 +673,24 @@ class B200WhisperModel:
 
     # -- the lockstep scheduler ------------------------------------------------------------------
     def _run_jobs(self, jobs: List[_StreamJob]) -> None:
-        """Advance all streams window by window; every device call covers every live stream."""
+        """Advance all streams window by window; every device call covers every live stream (in groups of at most
+        ``engine.max_streams``: the encoder slot pool holds 2 x max_streams windows, and a group's slots are handed
+        back explicitly before the next group / window is encoded -- never left to the garbage collector)."""
+        cap = int(getattr(self.model, "max_streams", 0) or 0) or len(jobs) or 1
         while True:
             windows = [(j, j.advance_window()) for j in jobs]
-            live = [(j, w) for j, w in windows if w is not None]
-            if not live:
+            live_all = [(j, w) for j, w in windows if w is not None]
+            if not live_all:
                 return
-            tm = getattr(self, "last_timing", None) or {}
-            t0 = time.perf_counter()
-            enc = self.encode(self._stack_windows([w for _, w in live]))
-            tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
+            for g0 in range(0, len(live_all), cap):
+                self._run_window_group(live_all[g0:g0 + cap])
+
+    def _run_window_group(self, live: List[Tuple[_StreamJob, np.ndarray]]) -> None:
+        tm = getattr(self, "last_timing", None) or {}
+        t0 = time.perf_counter()
+        enc = self.encode(self._stack_windows([w for _, w in live]))
+        tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
+        try:
             for k, (j, _) in enumerate(live):
                 j.enc = enc.select([k]) if hasattr(enc, "select") else _EncoderSlice(enc, k)
                 if j.opt.multilingual:
@@ -710,18 +718,32 @@ class B200WhisperModel:
                     t0 = time.perf_counter()
                     outs = self.model.generate(sub, [live[k][0].prompt for k in ks], **kw)
                     t1 = time.perf_counter()
+                    del sub
                     for k, r in zip(ks, outs):
                         if not live[k][0].accept(r):
                             nxt.append(k)
                     tm["generate"] = tm.get("generate", 0.0) + t1 - t0
                     tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
                 pending = sorted(nxt)
+            t0 = time.perf_counter()
+            self._align_windows([j for j, _ in live])
             for j, _ in live:
                 j.finish_window()
-                j.enc = None                      # give the encoder slots back before the next window
                 if j.single_window:
                     j.seek = j.content_frames     # bench switch: one 30 s window per chunk (pinned work)
+            tm["finish"] = tm.get("finish", 0.0) + time.perf_counter() - t0
+        finally:
+            for j, _ in live:
+                j.enc = None
+            release = getattr(enc, "release", None)
+            if release is not None:
+                release()                         # encoder slots back to the pool NOW (explicit, not refcount-driven)
             del enc
+
+    def _align_windows(self, jobs: List[_StreamJob]) -> None:
+        """Hook: batched word alignment of all streams of a window (K14).  The per-stream call inside
+        ``finish_window`` remains the fallback."""
+        return
 
     def _stack_windows(self, views: List[np.ndarray]) -> np.ndarray:
         """[B, n_mels, 3000] batch of zero-padded windows, written straight into a buffer that is reused from call to
