@@ -46,6 +46,14 @@ SCENARIOS = {
                                    kw=dict(temperature=[0.0], without_timestamps=True, prefix="hello",
                                            max_new_tokens=20, log_prob_threshold=None)),
     "en_silence": dict(model="micro.en", seed=0, audio=("silence", 2.0, 0), kw=dict(temperature=[0.0])),
+    # H8: VAD clipping + restore_speech_timestamps (reference :830-838, :1792-1817) with the deterministic stub detector
+    # (tests/stub_vad.py) standing in for Silero on BOTH sides
+    "en_vad_two_chunks": dict(model="micro.en", seed=0, audio=("gapped", (4.0, 3.5, 5.0), 6),
+                              kw=dict(temperature=[0.0], vad_filter=True, log_prob_threshold=None)),
+    "en_vad_words": dict(model="micro.en", seed=3, audio=("gapped", (3.0, 2.6, 2.5, 4.0, 3.0), 7),
+                         kw=dict(temperature=[0.0], vad_filter=True, word_timestamps=True, log_prob_threshold=None,
+                                 vad_parameters=dict(threshold=0.5, min_silence_duration_ms=1500))),
+    "en_vad_all_silence": dict(model="micro.en", seed=0, audio=("silence", 3.0, 0), kw=dict(temperature=[0.0], vad_filter=True)),
     "en_beam2_greedy_words": dict(model="micro.en", seed=3, audio=("speech", 7.5, 5),
                                   kw=dict(temperature=[0.0], beam_size=2, word_timestamps=True,
                                           log_prob_threshold=None, condition_on_previous_text=False)),
@@ -54,6 +62,9 @@ SCENARIOS = {
 
 def make_audio(spec):
     kind, sec, seed = spec
+    if kind == "gapped":   # speech, silence, speech, ... (seconds): what VAD gating exists for
+        parts = [synth.speech_like(d, seed=seed + i) if i % 2 == 0 else synth.silence(d) for i, d in enumerate(sec)]
+        return np.concatenate(parts).astype(np.float32)
     return synth.speech_like(sec, seed=seed) if kind == "speech" else synth.silence(sec)
 
 
@@ -94,9 +105,10 @@ def install_stubs():
         return next((w["end"] for s in reversed(segments) for w in reversed(s["words"])),
                     segments[-1]["end"] if segments else None)
     ut.get_end = get_end
+    from tests import stub_vad
     vad = _stub("faster_whisper.vad")
     for n in ("SpeechTimestampsMap", "VadOptions", "collect_chunks", "get_speech_timestamps"):
-        setattr(vad, n, None)
+        setattr(vad, n, getattr(stub_vad, n))
     fw.audio, fw.feature_extractor, fw.tokenizer, fw.utils, fw.vad = audio, fe, tk, ut, vad
 
 
@@ -143,7 +155,8 @@ def main():
             segments=None if segments is None else [seg_to_json(s) for s in segments],
             language=None if info is None else info.language,
             language_probability=None if info is None else float(info.language_probability),
-            duration=None if info is None else float(info.duration))
+            duration=None if info is None else float(info.duration),
+            duration_after_vad=None if info is None else float(info.duration_after_vad))
         print(name, None if segments is None else [(s.seek, round(s.start, 2), round(s.end, 2), s.temperature, len(s.tokens)) for s in segments])
     with open(os.path.join(HERE, "transcribe_reference.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -319,8 +319,11 @@ class _EngineStep:
             self.rows = [list(self.rows[0]) for _ in range(tokens.shape[0])]
         for r, row in enumerate(self.rows):
             row.extend(int(t) for t in tokens[r])
-        enc = self.enc_b.select([0] * len(self.rows))
-        out = self.eng.decode_logits(enc, self.rows)
+        out = []
+        cap = self.eng.max_streams
+        for r0 in range(0, len(self.rows), cap):      # at most max_streams rows per teacher-forced call
+            rows = self.rows[r0:r0 + cap]
+            out.extend(self.eng.decode_logits(self.enc_b.select([0] * len(rows)), rows))
         return torch.from_numpy(np.stack([o[-t_new:] for o in out]))
 
 

@@ -24,8 +24,9 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "transcribe_reference.j
 def _model(sc):
     dims = dims_for(sc["model"])
     eng = OracleWhisper(random_init(dims, seed=sc["seed"]), dims)
+    from tests import stub_vad
     return B200WhisperModel(sc["model"], engine=eng, hf_tokenizer=build_synthetic_tokenizer(dims.vocab),
-                            feature_extractor=OracleFeatureExtractor(dims.n_mels))
+                            feature_extractor=OracleFeatureExtractor(dims.n_mels), vad=stub_vad)
 
 
 def _check(segs, gold):
@@ -49,7 +50,12 @@ def test_transcribe_matches_reference_orchestration(name):
     gold = json.load(open(GOLD))[name]
     sc = SCENARIOS[name]
     segs, info = _model(sc).transcribe(make_audio(sc["audio"]), **sc["kw"])
+    if gold["segments"] is None:      # nothing left after VAD: (None, None) like reference :860-861
+        assert segs is None and info is None
+        return
     _check(segs, gold["segments"])
+    if sc["kw"].get("vad_filter"):
+        assert info.duration_after_vad == pytest.approx(gold["duration_after_vad"]) and info.duration_after_vad < info.duration
     assert info.language == gold["language"]
     assert float(info.language_probability) == pytest.approx(gold["language_probability"], abs=1e-6)
     assert info.duration == pytest.approx(gold["duration"])

@@ -471,7 +471,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
   s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
   s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
-  s.seed = dalloc<unsigned>(c, 1);
+  s.seed = dalloc<unsigned>(c, 1); s.steps_left = dalloc<int>(c, 1);
   s.pre_n = dalloc<int>(c, B); s.pre_last = dalloc<int>(c, B); s.pre_penult = dalloc<int>(c, B); s.pre_lts = dalloc<int>(c, B);
   WL_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
@@ -903,24 +903,53 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   decode_init(st, c->ds, so, vi, B, R);
   const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms, Kr);
 
+  // The whole token loop is ONE graph launch: a conditional WHILE node whose body is the captured decode step; the
+  // body's last kernel (loop_condition) keeps the loop alive while some stream is still decoding and the step budget
+  // lasts.  No host round trip per token (round 1 synchronised every 4 steps), no wasted steps after the last EOT.
+  // WLB200_LOOP_GRAPH=0 falls back to one graph launch per step with a host check every 4 steps.
+  static const bool loop_graph = [] { const char* e = getenv("WLB200_LOOP_GRAPH"); return e ? atoi(e) != 0 : true; }();
   cudaGraphExec_t exec = nullptr;
   long graph_kernels = 0;
+  bool is_loop = false;
   if (o->use_cuda_graph) {
     char key[160];
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
-             so.sampling, *(const unsigned*)&so.temperature);
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x/%d", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
+             so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
-      cudaGraph_t g;
       const long before = gemm_launch_count() + other_launch_count();
-      WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      try {
-        decode_step(c, B, Kr, so, vi, nsplit, false);
-      } catch (...) {
-        cudaStreamEndCapture(st, &g);
-        throw;
+      cudaGraph_t g = nullptr, cap = nullptr;
+      if (loop_graph) {
+        WL_CUDA(cudaGraphCreate(&g, 0));
+        cudaGraphConditionalHandle h;
+        WL_CUDA(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.conditional.handle = h;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        WL_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        WL_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        try {
+          decode_step(c, B, Kr, so, vi, nsplit, false);
+          loop_condition(st, c->ds, h, B);
+        } catch (...) {
+          cudaStreamEndCapture(st, &cap);
+          cudaGraphDestroy(g);
+          throw;
+        }
+        WL_CUDA(cudaStreamEndCapture(st, &cap));
+      } else {
+        WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          decode_step(c, B, Kr, so, vi, nsplit, false);
+        } catch (...) {
+          cudaStreamEndCapture(st, &g);
+          throw;
+        }
+        WL_CUDA(cudaStreamEndCapture(st, &g));
       }
-      WL_CUDA(cudaStreamEndCapture(st, &g));
       ge.kernels = gemm_launch_count() + other_launch_count() - before;
       c->capture_counted += ge.kernels;
       WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
@@ -928,26 +957,36 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     }
     exec = ge.exec;
     graph_kernels = ge.kernels;
+    is_loop = loop_graph;
   }
   ensure_host(c, (size_t)B * (T_MAX + 16) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
   int* h_done = c->h_int;  // reuse (prompts are already on the device: the copies above are stream-ordered)
   WL_CUDA(cudaStreamSynchronize(st));
-  int ran = 0;
-  const int check_every = 4;
-  while (ran < max_steps) {
-    const int n = std::min(check_every, max_steps - ran);
-    for (int i = 0; i < n; ++i) {
-      if (exec) {
-        WL_CUDA(cudaGraphLaunch(exec, st));
-        c->graph_launched += graph_kernels;
-      } else {
-        decode_step(c, B, Kr, so, vi, nsplit, false);
-      }
-    }
-    ran += n;
-    WL_CUDA(cudaMemcpyAsync(h_done, c->ds.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (is_loop) {
+    h_done[0] = max_steps;
+    WL_CUDA(cudaMemcpyAsync(c->ds.steps_left, h_done, sizeof(int), cudaMemcpyHostToDevice, st));
+    WL_CUDA(cudaGraphLaunch(exec, st));
+    WL_CUDA(cudaMemcpyAsync(h_done, c->ds.steps_left, sizeof(int), cudaMemcpyDeviceToHost, st));
     WL_CUDA(cudaStreamSynchronize(st));
-    if (*h_done >= B) break;
+    c->graph_launched += graph_kernels * (long)(max_steps - h_done[0]);
+  } else {
+    int ran = 0;
+    const int check_every = 4;
+    while (ran < max_steps) {
+      const int n = std::min(check_every, max_steps - ran);
+      for (int i = 0; i < n; ++i) {
+        if (exec) {
+          WL_CUDA(cudaGraphLaunch(exec, st));
+          c->graph_launched += graph_kernels;
+        } else {
+          decode_step(c, B, Kr, so, vi, nsplit, false);
+        }
+      }
+      ran += n;
+      WL_CUDA(cudaMemcpyAsync(h_done, c->ds.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      WL_CUDA(cudaStreamSynchronize(st));
+      if (*h_done >= B) break;
+    }
   }
   WL_CUDA(cudaEventRecord(c->ev1, st));
   // results

@@ -85,6 +85,7 @@ struct DecodeState {
   int* hyp_tok;      // [B][MAX_HYPS][T_MAX]
   int* steps_run;    // [B] decoder steps executed for the stream (diagnostics)
   int* n_done;       // [1] number of finished streams
+  int* steps_left;   // [1] decode steps the device-side loop may still run (conditional WHILE graph)
   unsigned* seed;    // [1] sampling seed of this generate call (device scalar: the captured graph does not depend on it)
   // teacher-forced mode (detect_language / align / logits test hook)
   int* force_len;    // [B] 0 = normal search; >0 = feed prompt only, then stop
@@ -129,6 +130,10 @@ int cross_attn_pick_nsplit(int B, int H, int num_sms, int rows_per_stream);
 // K12: per-row masked log-softmax + top candidates, then per-stream beam / greedy update.
 void search_rows(cudaStream_t st, const DecodeState& s, const float* logits, const SearchOpts& o, const VocabIds& v, int R);
 void search_streams(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B);
+
+// Last node of the loop body of the conditional WHILE graph: keep iterating while some stream is still decoding and the
+// step budget is not used up (one thread; it runs after search_streams, so n_done is final for this step).
+void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalHandle h, int B);
 
 // initialise the state for a generate call (prompts already uploaded)
 void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R);

@@ -492,6 +492,22 @@ void search_streams(cudaStream_t st, const DecodeState& s, const SearchOpts& o, 
   note_launch(1);
 }
 
+// ============================================================================ device-terminated decode loop
+__global__ void loop_condition_kernel(DecodeState s, cudaGraphConditionalHandle h, int B) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    const int left = *s.steps_left - 1;
+    *s.steps_left = left;
+    cudaGraphSetConditional(h, (left > 0 && *s.n_done < B) ? 1u : 0u);
+  }
+}
+void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalHandle h, int B) {
+  PdlScope no_pdl(false);   // a full dependency: every search_streams block has updated n_done
+  launch_kernel(loop_condition_kernel, dim3(1), dim3(32), 0, st, s, h, B);
+  note_launch(1);
+}
+
 // ============================================================================ init
 __global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v) {
   const int b = blockIdx.x, tid = threadIdx.x;
