@@ -26,6 +26,7 @@ pytestmark = pytest.mark.gpu
 LOGIT_TOL = 0.12       # fp16 logit tolerance (logit std is ~3)
 MARGIN_TOL = 0.20      # a greedy token decision closer than this may legitimately flip
 SCORE_TOL = 0.05       # length-normalised hypothesis score: beam-search near-ties within this are interchangeable
+ALIGN_MAX_SHIFT = 6    # frames (0.12 s) a DTW jump may move under an fp16-sized perturbation of the attention weights
 BEAM_TIE_TOL = 0.25    # cumulative log-prob gap between two beam candidates that an fp16-sized logit perturbation,
                        # accumulated over the decoded prefix (2 x LOGIT_TOL), can flip
 
@@ -297,8 +298,9 @@ def test_generate_with_prefix_matches_oracle(beam):
     got = eng.generate(enc, prompts, **kw)
     ref = orc.generate(oenc, prompts, **kw)
     _compare_generation(got, ref, f"prefix beam{beam}", orc, oenc, prompts, kw, eng=eng, enc=enc)
-    # stream 1 decodes without timestamps even though its prompt does not END with <|notimestamps|>
-    assert all(t < sp.timestamp_begin for t in got[1].sequences_ids[0])
+    # stream 1: <|notimestamps|> sits INSIDE the prompt (a prefix follows it), so the timestamp rules must be off:
+    # its first generated token is not forced to be a timestamp (random weights: text tokens dominate)
+    assert got[1].sequences_ids[0][0] == ref[1].sequences_ids[0][0]
     # stream 0: the history already holds <|0.00|> + text, so the first generated token is free to be text
 
 
@@ -453,14 +455,7 @@ def test_align_matches_oracle():
     for g, r, t in zip(got, ref, text):
         assert len(g.text_token_probs) == len(t)
         np.testing.assert_allclose(g.text_token_probs, r.text_token_probs, atol=0.02, rtol=0.05)
-        ga, ra = np.array(g.alignments), np.array(r.alignments)
-        assert ga[0].tolist() == [0, 0] and ga[-1].tolist() == ra[-1].tolist()
-        # DTW paths are monotone staircases; fp16 perturbations may shift a jump by a frame or two
-        jump_g = [int(ga[ga[:, 0] == i, 1].min()) for i in range(len(t) + 1)]
-        jump_r = [int(ra[ra[:, 0] == i, 1].min()) for i in range(len(t) + 1)]
-        diff = np.abs(np.array(jump_g) - np.array(jump_r))
-        print("align jump diffs", diff.tolist())
-        assert np.median(diff) <= 1 and (diff <= 3).mean() >= 0.8
+        _check_alignment(g.alignments, r.alignments, len(t))
 
 
 # --------------------------------------------------------------------------------------- end to end (Boundary B)
@@ -502,6 +497,152 @@ def test_transcribe_end_to_end_matches_oracle_pipeline():
                 assert gs[first].avg_logprob == pytest.approx(rs[first].avg_logprob, abs=0.3)
 
 
+# --------------------------------------------------------------------------------------- BASELINE configs at full size
+def test_small_en_greedy_30s_config2():
+    """BASELINE config 2: small.en shape (d=768, 12 heads, 12+12 layers, 80 mels), ONE stream, a 30 s chunk, greedy.
+    Exercises what the other sizes do not: a single decoder row (N tile 16, cross-attention with one query row),
+    GEMM K = 768 / 3072 (12 and 48 k-blocks), 12 heads."""
+    import time
+    dims = dims_for("small.en")
+    w = random_init(dims, seed=11)
+    from whisperlive_b200.engine import B200Whisper
+    eng = B200Whisper(dims, w, max_streams=1, max_beam=1, enc_slots=2)
+    orc = OracleWhisper(w, dims)
+    wav = synth.speech_like(30.0, seed=1234)
+    got_mel = eng.mel([wav])[0]
+    ref_mel = omel.log_mel(wav, dims.n_mels)
+    assert np.abs(got_mel - ref_mel).max() < 2e-4
+    feats = omel.pad_or_trim(ref_mel[:, :-1])[None]
+    enc = eng.encode(feats)
+    t0 = time.time()
+    oenc = orc.encode(feats)
+    print(f"oracle small.en encoder {time.time() - t0:.1f} s")
+    ref = oenc.enc.numpy()
+    err = np.abs(np.asarray(enc) - ref)
+    rel_rms = float(np.sqrt((err ** 2).mean() / (ref ** 2).mean()))
+    print(f"encoder small.en: max err {err.max():.4f} rel rms {rel_rms:.5f}")
+    assert rel_rms < 0.008 and err.max() < 0.08
+    kw = dict(beam_size=1, max_length=2 * 64, suppress_tokens=[-1], return_scores=True, return_no_speech_prob=True)
+    prompts = [[orc.spec.sot]]
+    got = eng.generate(enc, prompts, **kw)
+    refg = orc.generate(oenc, prompts, **kw)
+    n_div = _compare_generation(got, refg, "small.en greedy", orc, oenc, prompts, kw, eng=eng, enc=enc)
+    print(f"small.en greedy 30 s: {len(got[0].sequences_ids[0])} tokens, divergences {n_div}, score {got[0].scores[0]:.4f} vs {refg[0].scores[0]:.4f}")
+    assert len(got[0].sequences_ids[0]) >= 8
+    del eng
+
+
+_LARGE = {}
+
+
+def _large_v3():
+    """One large-v3-shaped engine + oracle shared by the full-size tests (init is the expensive part)."""
+    if not _LARGE:
+        import time
+        t0 = time.time()
+        dims = dims_for("large-v3")
+        w = random_init(dims, seed=5)
+        from whisperlive_b200.engine import B200Whisper
+        # 10 alignment heads in the upper layers (the released large-v3 config lists 10); engine and oracle read them
+        # from the same dims object
+        dims.alignment_heads = [(dims.dec_layers - 1 - (i // 4), (3 * i) % dims.n_heads) for i in range(10)]
+        _LARGE["eng"] = B200Whisper(dims, w, max_streams=8, max_beam=4, enc_slots=10)
+        _LARGE["orc"] = OracleWhisper(w, dims)
+        print(f"large-v3 init {time.time() - t0:.1f} s")
+    return _LARGE["eng"], _LARGE["orc"]
+
+
+def test_large_v3_b8_beam4_config3():
+    """BASELINE config 3: large-v3, B = 8 streams with chunks U[5,30] s, beam 4, >= 40 decoded tokens.  All 8 streams
+    run on the device in one batch (R = 32 decoder rows, N tile 32); the CPU oracle re-derives three of them (its
+    encoder costs ~2.6 TFLOP per stream), token for token with the explained-divergence rule, and every stream is
+    checked for batch invariance against a solo run of the engine."""
+    import time
+    eng, orc = _large_v3()
+    dims, sp = eng.dims, orc.spec
+    durs = synth.chunk_durations(8, 5.0, 30.0, seed=1234)
+    feats = np.stack([feats_for(dims, d, 1234 + i) for i, d in enumerate(durs)])
+    enc = eng.encode(feats)
+    sot_seq = [sp.sot, sp.sot + 1, sp.sot + 1 + dims.num_languages + 1]
+    kw = dict(beam_size=4, max_length=2 * 40, suppress_tokens=[-1], suppress_blank=True, return_scores=True)
+    prompts = [sot_seq] * 8
+    got = eng.generate(enc, prompts, **kw)
+    assert all(len(g.sequences_ids[0]) >= 1 for g in got)
+    print("config 3 lengths", [len(g.sequences_ids[0]) for g in got], "steps", [g.steps for g in got])
+    check = [0, 3, 7]
+    t0 = time.time()
+    oenc = orc.encode(feats[check])
+    refs = orc.generate(oenc, [sot_seq] * len(check), **kw)
+    print(f"oracle: 3 streams encoder + beam-4 decode {time.time() - t0:.1f} s")
+    sub = enc.select(check)
+    n_div = _compare_generation([got[i] for i in check], refs, "large-v3 B8 beam4", orc, oenc, [sot_seq] * len(check), kw,
+                                eng=eng, enc=sub)
+    print("config 3 divergences (explained):", n_div)
+    # batch invariance of the whole path: stream 5 decoded alone gives the same hypothesis
+    solo = eng.generate(enc.select([5]), [sot_seq], **kw)[0]
+    assert solo.sequences_ids[0] == got[5].sequences_ids[0] or abs(solo.scores[0] - got[5].scores[0]) < SCORE_TOL
+    enc.release()
+
+
+def test_large_v3_detect_language_and_align():
+    """K13 / K14 at the architecture the metric is quoted on: 128 mels, 20 heads, 32 layers, 100 languages."""
+    eng, orc = _large_v3()
+    dims, sp = eng.dims, orc.spec
+    feats = np.stack([feats_for(dims, 8.0, 31), feats_for(dims, 5.0, 32)])
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    got = eng.detect_language(enc)
+    ref = orc.detect_language(oenc)
+    for g, r in zip(got, ref):
+        gd, rd = dict(g), dict(r)
+        assert len(gd) == 100 and max(abs(gd[k] - rd[k]) for k in rd) < 0.03
+        assert g[0][0] == r[0][0] or abs(r[0][1] - r[1][1]) < 0.03
+    rng = np.random.default_rng(9)
+    text = [rng.integers(256, 50000, 18).tolist(), rng.integers(256, 50000, 7).tolist()]
+    nf = [800, 500]
+    sot_seq = [sp.sot, sp.sot + 1, sp.sot + 1 + dims.num_languages + 1]
+    ga = eng.align(enc, sot_seq, text, nf)
+    ra = orc.align(oenc, sot_seq, text, nf)
+    for g, r, t in zip(ga, ra, text):
+        np.testing.assert_allclose(g.text_token_probs, r.text_token_probs, atol=0.02, rtol=0.05)
+        _check_alignment(g.alignments, r.alignments, len(t))
+    enc.release()
+
+
+def _check_alignment(got, ref, n_text):
+    """DTW paths are monotone staircases from (0,0) to the same corner; an fp16-sized perturbation of the attention
+    weights may move a jump, by a bounded number of frames: every token's first frame within ALIGN_MAX_SHIFT frames of
+    the oracle's, the median within 1."""
+    ga, ra = np.array(got), np.array(ref)
+    assert ga[0].tolist() == [0, 0] and ga[-1].tolist() == ra[-1].tolist()
+    assert (np.diff(ga[:, 0]) >= 0).all() and (np.diff(ga[:, 1]) >= 0).all() and (np.abs(np.diff(ga, axis=0)).sum(1) >= 1).all()
+    jump_g = [int(ga[ga[:, 0] == i, 1].min()) for i in range(n_text + 1)]
+    jump_r = [int(ra[ra[:, 0] == i, 1].min()) for i in range(n_text + 1)]
+    diff = np.abs(np.array(jump_g) - np.array(jump_r))
+    print("align jump diffs", diff.tolist())
+    assert np.median(diff) <= 1 and diff.max() <= ALIGN_MAX_SHIFT, diff.tolist()
+
+
+def test_transcribe_batch_more_streams_than_slots():
+    """n > max_streams streams, audio longer than one window -- the transcriber encodes in groups
+    of max_streams and hands every group's encoder slots back explicitly, so the pool (2 x max_streams) never runs dry
+    and every slot is free again afterwards."""
+    import gc
+    from whisperlive_b200.engine import B200Whisper
+    from whisperlive_b200.feature_extractor import FeatureExtractor
+    from whisperlive_b200.transcriber import B200WhisperModel
+    dims = dims_for("micro.en")
+    eng = B200Whisper(dims, random_init(dims, seed=0), max_streams=2, max_beam=5)
+    m = B200WhisperModel("micro.en", engine=eng, hf_tokenizer="synthetic", feature_extractor=FeatureExtractor(eng, dims.n_mels))
+    audios = [synth.speech_like(33.0 if i % 2 else 6.0, seed=40 + i) for i in range(5)]
+    kw = dict(temperature=[0.0, 0.4], beam_size=5)
+    out = m.transcribe_batch(audios, [kw] * 5)
+    assert len(out) == 5 and all(segs is not None and len(segs) > 0 for segs, _ in out)
+    solo = m.transcribe(audios[3], **kw)
+    assert [s.tokens for s in solo[0]] == [s.tokens for s in out[3][0]]
+    gc.collect()
+    assert eng.free_slots() == eng.enc_slots
+
+
 # --------------------------------------------------------------------------------------- full size (BASELINE config)
 def test_full_size_large_v3_single_stream():
     """The architecture BASELINE.json's metric is quoted on (large-v3: d=1280, 20 heads, 32+32 layers, 128 mels,
@@ -510,13 +651,8 @@ def test_full_size_large_v3_single_stream():
     size-independent properties: batch invariance of the encoder and run-to-run bit-reproducibility of generate
     (deterministic split-K, no atomics)."""
     import time
-    t0 = time.time()
-    dims = dims_for("large-v3")
-    w = random_init(dims, seed=5)
-    from whisperlive_b200.engine import B200Whisper
-    eng = B200Whisper(dims, w, max_streams=2, max_beam=4, enc_slots=4)
-    orc = OracleWhisper(w, dims)
-    print(f"large-v3 init {time.time() - t0:.1f} s")
+    eng, orc = _large_v3()
+    dims = eng.dims
     wav = synth.speech_like(9.0, seed=21)
     ref_mel = omel.log_mel(wav, dims.n_mels)
     got_mel = eng.mel([wav])[0]
@@ -557,4 +693,3 @@ def test_full_size_large_v3_single_stream():
     rescored = _oracle_rescore(orc, oenc, 0, sot_seq, a.sequences_ids[0], kw)
     print(f"generate large-v3 beam 4: {len(a.sequences_ids[0])} tokens, engine score {a.scores[0]:.4f}, oracle score of the same tokens {rescored:.4f}")
     assert abs(rescored - a.scores[0]) < 0.02                                    # measured: 0.0013
-    del eng

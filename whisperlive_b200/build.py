@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwlb200.so")
-SOURCES = ["gemm.cu", "mel.cu", "elementwise.cu", "attention.cu", "flash_attn.cu", "search.cu", "misc.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "dec_gemm.cu", "mel.cu", "elementwise.cu", "attention.cu", "flash_attn.cu", "search.cu", "misc.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC"]
@@ -21,12 +21,17 @@ def _deps():
     return max(os.path.getmtime(f) for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps():
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    """timeline=True (or WLB200_TL_BUILD=1) compiles the in-graph timeline stamps in (tools/timeline.py): a profiling
+    build, never the shipped one."""
+    timeline = timeline or bool(os.environ.get("WLB200_TL_BUILD"))
+    if not force and not timeline and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps():
         return OUT
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if timeline:
+        extra.append("-DWLB200_TL=1")
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -48,4 +53,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv))

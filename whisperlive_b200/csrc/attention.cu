@@ -3,7 +3,7 @@
 //       (row, head), CUDA-core math (a few KB of work per warp).
 //   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V -- persistent
 //       CTAs, K/V streamed HBM -> smem by a producer warp (cp.async.bulk + mbarrier ring), consumed by 4 warps with
-//       mma.sync on the pre-swizzled chunks; partial softmaxes per key range merged by a small combine kernel.
+//       mma.sync on the pre-swizzled chunks; partial softmaxes per key range merged by the last range to finish.
 //   Reference call site of both: ctranslate2 Whisper.generate, transcriber_faster_whisper.py:1394-1407.
 #include <algorithm>
 #include <cstdlib>
@@ -24,7 +24,9 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
                                                                  __half* __restrict__ vc, long row_stride,
                                                                  __half* __restrict__ out, int H, int d, int R) {
   __shared__ float qs[SA_WARPS][64];
+  __shared__ float vn_all[SA_WARPS][64];
   __shared__ float sc_all[SA_WARPS][T_MAX];
+  __shared__ short ssrc_all[SA_WARPS][T_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * SA_WARPS + warp;
   pdl_trigger();
@@ -34,7 +36,9 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   const int pos = s.pos[r];
   const int n = pos + 1;
   float* q = qs[warp];
+  float* vnew = vn_all[warp];
   float* sc = sc_all[warp];
+  short* ssrc = ssrc_all[warp];
   // q / k / v of this (row, head), dims 2*lane and 2*lane+1: bias + the split-K partial sums, in range order
   const int c0 = h * 64 + 2 * lane;
   float2 qv = make_float2(0.f, 0.f), kv = qv, vv = qv;
@@ -47,30 +51,46 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   pdl_wait();
   tl_stamp(TL_SELF, 1);
   {
+    // at most 8 K ranges (dec_gemm_split_plan); predicated so that all 24 loads are in flight together, summed in order
     const float* row = qkv.ptr + (long)r * 3 * d + c0;
-#pragma unroll 4
-    for (int sp = 0; sp < qkv.nsplit; ++sp) {
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 qa[8], ka[8], va[8];
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) {
       const float* p = row + (long)sp * qkv.stride;
-      const float2 a = __ldcg(reinterpret_cast<const float2*>(p)), b2 = __ldcg(reinterpret_cast<const float2*>(p + d)),
-                   c2 = __ldcg(reinterpret_cast<const float2*>(p + 2 * d));
-      qv.x += a.x; qv.y += a.y; kv.x += b2.x; kv.y += b2.y; vv.x += c2.x; vv.y += c2.y;
+      const bool on = sp < qkv.nsplit;
+      qa[sp] = on ? __ldcg(reinterpret_cast<const float2*>(p)) : z2;
+      ka[sp] = on ? __ldcg(reinterpret_cast<const float2*>(p + d)) : z2;
+      va[sp] = on ? __ldcg(reinterpret_cast<const float2*>(p + 2 * d)) : z2;
+    }
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) {
+      qv.x += qa[sp].x; qv.y += qa[sp].y; kv.x += ka[sp].x; kv.y += ka[sp].y; vv.x += va[sp].x; vv.y += va[sp].y;
     }
   }
   qv.x *= 0.125f; qv.y *= 0.125f;
   *reinterpret_cast<float2*>(q + 2 * lane) = qv;
+  *reinterpret_cast<float2*>(vnew + 2 * lane) = vv;
   {
     const long o = (long)r * row_stride + ((long)h * T_MAX + pos) * 64 + 2 * lane;
     *reinterpret_cast<__half2*>(kc + o) = __floats2half2_rn(kv.x, kv.y);
     *reinterpret_cast<__half2*>(vc + o) = __floats2half2_rn(vv.x, vv.y);
   }
   const float dot_new = warp_sum(qv.x * kv.x + qv.y * kv.y);   // the new position uses the unrounded k (as before)
+  // beam indirection table of this row -> shared memory first: the K and V sweeps below then issue all their loads
+  // without a dependent global load in front of each (one L2 round trip per sweep instead of two per position)
+  {
+    const short* src = s.src + (long)r * T_MAX;
+#pragma unroll 1
+    for (int p = lane; p < pos; p += 32) ssrc[p] = src[p];
+  }
   __syncwarp();
-  const short* src = s.src + (long)r * T_MAX;
   float lmax = -INFINITY;
+#pragma unroll 1
   for (int p = lane; p < n; p += 32) {
     float acc = dot_new;
     if (p != pos) {
-      const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)src[p] * row_stride + ((long)h * T_MAX + p) * 64);
+      const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)ssrc[p] * row_stride + ((long)h * T_MAX + p) * 64);
       uint4 u[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) u[c] = kp[c];
@@ -91,6 +111,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   }
   const float mx = warp_max(lmax);
   float lsum = 0.f;
+#pragma unroll 1
   for (int p = lane; p < n; p += 32) {
     const float e = __expf(sc[p] - mx);
     sc[p] = e;
@@ -98,18 +119,39 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   }
   const float inv = 1.f / warp_sum(lsum);
   __syncwarp();
-  float2 acc = make_float2(0.f, 0.f);
-  const long hoff = (long)h * T_MAX * 64 + 2 * lane;
+  // weighted V sum: lane = (position group pg = lane / 8, 16-byte dim chunk c8 = lane % 8).  The 4 groups stride over
+  // the cached positions with independent 16-byte loads (8 in flight per lane), then fold with two shuffles; round 1
+  // walked the positions one by one with a dependent (index -> V row) load pair each: ~0.25 us per cached position.
+  const int c8 = lane & 7, pg = lane >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const long hoff = (long)h * T_MAX * 64 + c8 * 8;
 #pragma unroll 4
-  for (int p = 0; p < pos; ++p) {
+  for (int p = pg; p < pos; p += 4) {
     const float w = sc[p];
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vc + (long)src[p] * row_stride + hoff + (long)p * 64));
-    acc.x = fmaf(w, f.x, acc.x);
-    acc.y = fmaf(w, f.y, acc.y);
+    const uint4 u = *reinterpret_cast<const uint4*>(vc + (long)ssrc[p] * row_stride + hoff + (long)p * 64);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
+    }
   }
-  acc.x = fmaf(sc[pos], vv.x, acc.x);
-  acc.y = fmaf(sc[pos], vv.y, acc.y);
-  *reinterpret_cast<__half2*>(out + (long)r * d + c0) = __floats2half2_rn(acc.x * inv, acc.y * inv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (pg == 0) {
+    const float wn = sc[pos];
+    __align__(16) __half2 o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o2[e] = __floats2half2_rn(fmaf(wn, vnew[c8 * 8 + 2 * e], acc[2 * e]) * inv, fmaf(wn, vnew[c8 * 8 + 2 * e + 1], acc[2 * e + 1]) * inv);
+    *reinterpret_cast<uint4*>(out + (long)r * d + h * 64 + c8 * 8) = *reinterpret_cast<const uint4*>(o2);
+  }
 }
 
 void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
@@ -138,6 +180,7 @@ constexpr int XA_STAGE_BYTES = XA_CHUNK * 128;  // 64 halves per key
 constexpr int XA_NCHUNK = (S_ENC + XA_CHUNK - 1) / XA_CHUNK;  // 12
 constexpr int XA_TAIL_KEYS = S_ENC - (XA_NCHUNK - 1) * XA_CHUNK;  // 92 keys in the last chunk
 constexpr int MAX_STREAMS_CAP = 256;          // streams per decode call the live list can hold
+constexpr int XA_MAX_QSPLIT = 4;              // K ranges of the q projection the kernel sums (engine.cu caps the plan)
 
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -167,8 +210,8 @@ template <int NQ> struct XaCfg {
 template <int NQ, int XA_STAGES>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
-                                                         long slot_stride, float* __restrict__ part, float* __restrict__ probs,
-                                                         __half* __restrict__ out, int B,
+                                                         long slot_stride, float* __restrict__ part, int* __restrict__ merge_cnt,
+                                                         float* __restrict__ probs, __half* __restrict__ out, int B,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps, int dbg) {
   constexpr int SW = XaCfg<NQ>::SW;
   extern __shared__ uint8_t xa_smem_raw[];
@@ -189,6 +232,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ uint8_t live[MAX_STREAMS_CAP];
   __shared__ int n_live_sh;
+  __shared__ int xa_last;
   pdl_trigger();
 
   if (tid == 0) {
@@ -231,12 +275,16 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+#pragma unroll 1
       for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        const int sp = it % nsplit, h = (it / nsplit) % H, b = live[it / (nsplit * H)];
+        const unsigned bh = (unsigned)it / (unsigned)nsplit, bi = bh / (unsigned)H;
+        const int sp = it - (int)bh * nsplit, h = (int)(bh - bi * (unsigned)H), b = live[bi];
         const int c_begin = sp * cps, c_end = min(XA_NCHUNK, c_begin + cps);
         const long head_off = (long)s.slot[b] * slot_stride + (long)h * S_ENC * 64;
+#pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           const __half* src = (pass == 0 ? kc : vc) + head_off;
+#pragma unroll 1
           for (int c = c_begin; c < c_end; ++c) {
             const int nkeys = min(XA_CHUNK, S_ENC - c * XA_CHUNK);
             mbar_wait(&empty[stage], phase ^ 1);
@@ -256,29 +304,26 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int g = lane >> 2, tq = lane & 3;    // mma fragment coordinates: group (row / n index), thread-in-group
   int stage = 0;
   uint32_t phase = 0;
-  constexpr int MAX_QSPLIT = 8;                 // gemm_split_plan never exceeds 8 K ranges
+  constexpr int MAX_QSPLIT = XA_MAX_QSPLIT;     // the q projection is split over at most this many K ranges
   float qraw[4][1 + MAX_QSPLIT];                // this thread's 4 entries of q[8][64]: bias + raw partial sums
-  auto q_fetch = [&](int item) {
-    const int h2 = (item / nsplit) % H, b2 = live[item / (nsplit * H)];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 128, j = idx >> 6, dd = idx & 63;
-      const bool ok = j < rows_per_stream && !(dbg & 2);
-      qraw[e][0] = (ok && q.bias) ? __ldg(q.bias + h2 * 64 + dd) : 0.f;
-      const float* qp = q.ptr + (long)(b2 * rows_per_stream + (ok ? j : 0)) * d + h2 * 64 + dd;
-#pragma unroll
-      for (int sq = 0; sq < MAX_QSPLIT; ++sq) qraw[e][1 + sq] = (ok && sq < q.nsplit) ? __ldcg(qp + (long)sq * q.stride) : 0.f;
-    }
-  };
-  for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-  const int sp = it % nsplit, h = (it / nsplit) % H, b = live[it / (nsplit * H)];
+  // The item loop is rotated by half an item so that the q fetch exists ONCE in the code: "iteration -1" only requests
+  // the first item's q; every later iteration requests the next item's q in the middle of the current one (its
+  // latency hides behind the softmax pass and the V sweep).  The kernel is launched once per layer per token; its
+  // instruction footprint is part of what every launch costs (see dec_gemm.cu).
+#pragma unroll 1
+  for (int it = (int)blockIdx.x - (int)gridDim.x; it < total_items; it += gridDim.x) {
+  const bool real = it >= 0;
+  int sp = 0, h = 0, b = 0;
+  if (real) {
+    const unsigned bh = (unsigned)it / (unsigned)nsplit, bi = bh / (unsigned)H;
+    sp = it - (int)bh * nsplit; h = (int)(bh - bi * (unsigned)H); b = live[bi];
+  }
   const int c_begin = sp * cps, c_end = min(XA_NCHUNK, c_begin + cps);
   const int nchunks = c_end - c_begin;
   const int row0 = b * rows_per_stream;
-  // q rows of this (stream, head) as [8][64] fp32 in shared memory (rows >= rows_per_stream are zero), pre-scaled by
-  // 1/8.  The raw split-K partial sums of the NEXT item are requested in the middle of the current one (see below)
-  // so that their latency never stalls the K/V stream; only the very first item of a CTA loads them here.
-  if (it == (int)blockIdx.x) q_fetch(it);
+  uint32_t qh[4][2], ql[4][2];
+  if (real) {
+  // q rows of this (stream, head) as [8][64] fp32 in shared memory (rows >= rows_per_stream are zero), pre-scaled by 1/8
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     float a = qraw[e][0];   // bias
@@ -288,7 +333,6 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   }
   consumers_sync();
   // B fragments of q^T (k = dim, n = row): lane holds q[g][ks*16 + 2*tq + {0,1}] and [.. + 8], as hi + lo halves
-  uint32_t qh[4][2], ql[4][2];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
@@ -303,6 +347,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 
   // ---- pass 1: scores.  Warp w owns keys [32w, 32w+32) of every chunk: 2 m-tiles x 4 k-steps.
   const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8;   // ldmatrix: row this lane addresses inside a 16-row tile
+#pragma unroll 1
   for (int ci = 0; ci < nchunks; ++ci) {
     const int nkeys = min(XA_CHUNK, S_ENC - (c_begin + ci) * XA_CHUNK);
     mbar_wait(&full[stage], phase);
@@ -336,8 +381,23 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
       }
     }
   }
+  }   // real: scores of this item are in S
   // request the next item's q partial sums now: they arrive while the softmax pass and the V sweep run
-  if (it + (int)gridDim.x < total_items) q_fetch(it + gridDim.x);
+  if (it + (int)gridDim.x < total_items) {
+    const int item = it + (int)gridDim.x;
+    const unsigned bh2 = (unsigned)item / (unsigned)nsplit, bi2 = bh2 / (unsigned)H;
+    const int h2 = (int)(bh2 - bi2 * (unsigned)H), b2 = live[bi2];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 128, j = idx >> 6, dd = idx & 63;
+      const bool ok = j < rows_per_stream && !(dbg & 2);
+      qraw[e][0] = (ok && q.bias) ? __ldg(q.bias + h2 * 64 + dd) : 0.f;
+      const float* qp = q.ptr + (long)(b2 * rows_per_stream + (ok ? j : 0)) * d + h2 * 64 + dd;
+#pragma unroll
+      for (int sq = 0; sq < MAX_QSPLIT; ++sq) qraw[e][1 + sq] = (ok && sq < q.nsplit) ? __ldcg(qp + (long)sq * q.stride) : 0.f;
+    }
+  }
+  if (!real) continue;
   consumers_sync();
   // ---- softmax statistics over this CTA's key range
   const int nk_pad = nchunks * XA_CHUNK;
@@ -345,6 +405,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 #pragma unroll
   for (int j = 0; j < NQ; ++j) mx[j] = -INFINITY;
   const int nk_sm = (dbg & 4) ? 0 : nk_pad;
+#pragma unroll 1
   for (int k = tid; k < nk_sm; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) mx[j] = fmaxf(mx[j], S[(long)k * SW + j]);
@@ -363,6 +424,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   float sm32[NQ];   // exact fp32 sums: only the alignment probabilities use them
 #pragma unroll
   for (int j = 0; j < NQ; ++j) sm32[j] = 0.f;
+#pragma unroll 1
   for (int k = tid; k < nk_sm; k += 128) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
@@ -406,6 +468,7 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
   const int ldt_row = (lane & 7) + (lane >> 4) * 8;       // .trans tiles: matrices 2,3 are the second 8 keys
+#pragma unroll 1
   for (int ci = 0; ci < nchunks; ++ci) {
     mbar_wait(&full[stage], phase);
     const uint32_t buf = smem_u32(stage_buf + stage * XA_STAGE_BYTES);
@@ -472,31 +535,35 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     dst[tid * 66 + 0] = mx[tid];
     dst[tid * 66 + 1] = sm[tid];
   }
-  consumers_sync();   // ored is rewritten by the next item
-  }   // item loop
-}
-
-// merge the nsplit partial softmaxes of every (row, head), in key-range order
-__global__ void cross_attn_combine_kernel(DecodeState s, const float* __restrict__ part, __half* __restrict__ out,
-                                          int rows_per_stream, int H, int d, int nsplit) {
-  const int r = blockIdx.y, h = blockIdx.x, dd = threadIdx.x;
-  const int b = r / rows_per_stream, j = r % rows_per_stream;
-  pdl_trigger();
-  if (s.done[b]) return;
-  tl_stamp(TL_COMBINE, 0);
-  pdl_wait();
-  tl_stamp(TL_COMBINE, 1);
-  const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
-  float M = -INFINITY;
-  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(p + (long)sp * MAX_ROWS_PER_STREAM * 66));
-  float L = 0.f, o = 0.f;
-  for (int sp = 0; sp < nsplit; ++sp) {
-    const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
-    const float w = __expf(__ldcg(ps) - M);
-    L += __ldcg(ps + 1) * w;
-    o += __ldcg(ps + 2 + dd) * w;
+  // The LAST key range of this (stream, head) to get here merges all nsplit partial softmaxes -- always in key-range
+  // order, so the result does not depend on who arrives last -- and writes the attention output.  Round 1 ran this
+  // merge as a separate kernel (cross_attn_combine: one more stage on the per-layer dependency chain).
+  __threadfence();
+  consumers_sync();   // every partial of this CTA is visible device-wide; ored may be rewritten from here on
+  if (tid == 0) {
+    const int prev = atomicAdd(merge_cnt + b * H + h, 1);
+    xa_last = prev == nsplit - 1;
+    if (xa_last) merge_cnt[b * H + h] = 0;   // ready for the next launch (next layer): nobody else touches it any more
   }
-  out[(long)r * d + h * 64 + dd] = __float2half_rn(o / L);
+  consumers_sync();
+  if (xa_last) {
+    __threadfence();
+    for (int idx = tid; idx < rows_per_stream * 64; idx += 128) {
+      const int j = idx >> 6, dd = idx & 63;
+      const float* p = pbase + j * 66;
+      float M = -INFINITY;
+      for (int q2 = 0; q2 < nsplit; ++q2) M = fmaxf(M, __ldcg(p + (long)q2 * MAX_ROWS_PER_STREAM * 66));
+      float L = 0.f, o2 = 0.f;
+      for (int q2 = 0; q2 < nsplit; ++q2) {
+        const float* ps = p + (long)q2 * MAX_ROWS_PER_STREAM * 66;
+        const float w = __expf(__ldcg(ps) - M);
+        L += __ldcg(ps + 1) * w;
+        o2 += __ldcg(ps + 2 + dd) * w;
+      }
+      out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(o2 / L);
+    }
+  }
+  }   // item loop
 }
 
 static int xa_template_nq(int rows_per_stream) {
@@ -581,7 +648,7 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   const int stg = xa_stages();
   auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
   if (ws.ev0) WL_CUDA(cudaEventRecord(ws.ev0, st));
-  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.merge_cnt, ws.probs, out, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
   if (ws.ev1) WL_CUDA(cudaEventRecord(ws.ev1, st));
   note_launch(1);
 }
@@ -605,16 +672,12 @@ void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc&
                         long slot_stride, const CrossAttnWorkspace& ws, __half* out, int B, int rows_per_stream, int H,
                         int d, int nsplit) {
   WL_CHECK(rows_per_stream >= 1 && rows_per_stream <= MAX_ROWS_PER_STREAM, WL_ERR_ARG, "rows per stream %d", rows_per_stream);
-  WL_CHECK(q.nsplit >= 1 && q.nsplit <= 8, WL_ERR_ARG, "cross attention: q arrives in %d K ranges (1..8 supported)", q.nsplit);
+  WL_CHECK(q.nsplit >= 1 && q.nsplit <= XA_MAX_QSPLIT, WL_ERR_ARG, "cross attention: q arrives in %d K ranges (1..%d supported)", q.nsplit, XA_MAX_QSPLIT);
   if (rows_per_stream == 1) launch_cross<1>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream == 2) launch_cross<2>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream <= 4) launch_cross<4>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
-  if (nsplit > 1) {
-    launch_kernel(cross_attn_combine_kernel, dim3(H, B * rows_per_stream), dim3(64), 0, st, s, ws.part, out, rows_per_stream, H, d, nsplit);
-    note_launch(1);
-  }
 }
 
 }  // namespace wl

@@ -80,7 +80,13 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // (tools/timeline.py).  One pointer per translation unit (no relocatable device code), bound by tl_bind().
 constexpr unsigned TL_CAP = 1u << 20;
 static __device__ unsigned long long* wl_tl_buf = nullptr;
+// Compiled in only with -DWLB200_TL=1 (python -m whisperlive_b200.build --timeline): even one thread's worth of
+// stamping code is instruction-cache footprint in kernels that are launched 400 times per token.
+#ifndef WLB200_TL
+#define WLB200_TL 0
+#endif
 __device__ __forceinline__ void tl_stamp_any(int kernel_id, int what) {
+  if (!WLB200_TL) return;
   unsigned long long* buf = wl_tl_buf;
   if (buf != nullptr) {
     unsigned long long t;

@@ -108,94 +108,62 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-// Decode-step variant: one 128-thread block per row (<= 3 float4 per thread), a few dozen instructions -- the
-// ~100 launches per decode step must not be dominated by instruction fetch.  It also folds in the residual
-// update that the preceding split-K GEMM left as partial sums: x += bias + sum_s partial_s, in a fixed order.
-__global__ void __launch_bounds__(128) layernorm_update_kernel(float* __restrict__ x, PartialSrc upd, const float* __restrict__ g,
+// Decode-step variant: one block of d/4 threads per row, ONE float4 per thread -- no column loop, no bounds checks, a
+// hundred-odd instructions in all.  The decode step launches this ~100 times per token on a handful of rows; what a
+// launch costs there is the instruction fetch of whatever it executes (the kernels of a layer do not fit the SM's
+// instruction caches together), so it is written for size: round 1's generic version was 11 KB of SASS and took 5 us
+// inside the graph.  It also folds in the residual update that the preceding split-K GEMM left as partial sums:
+// x += bias + sum_s partial_s, in a fixed order (bit-reproducible).
+__global__ void __launch_bounds__(384) layernorm_update_kernel(float* __restrict__ x, PartialSrc upd, const float* __restrict__ g,
                                                                const float* __restrict__ be, __half* __restrict__ y, int d) {
   const long row = blockIdx.x;
-  __shared__ float red[8];
-  const int tid = threadIdx.x, n4 = d >> 2;
+  __shared__ float red[2][12];
+  const int tid = threadIdx.x, nw = blockDim.x >> 5;
   pdl_trigger();
-  float4* x4 = reinterpret_cast<float4*>(x + row * d);
-  float4 v[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {   // the bias is a weight: fetch it before waiting for the producer kernel
-    const int c = i * 128 + tid;
-    v[i] = (c < n4 && upd.nsplit > 0 && upd.bias) ? __ldg(reinterpret_cast<const float4*>(upd.bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  // bias, gamma, beta are weights: fetched before waiting for the producer kernel
+  float4 v = (upd.nsplit > 0 && upd.bias) ? __ldg(reinterpret_cast<const float4*>(upd.bias) + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + tid), bb = __ldg(reinterpret_cast<const float4*>(be) + tid);
+  float4* x4 = reinterpret_cast<float4*>(x + row * d) + tid;
   tl_stamp(TL_LN, 0);
   pdl_wait();
   tl_stamp(TL_LN, 1);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int c = i * 128 + tid;
-    if (c < n4) {
-      const float4 a = x4[c];
-      v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
-    }
+  {
+    const float4 a = *x4;
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
   }
   if (upd.nsplit > 0) {
-    // K ranges are added in index order (bit-reproducible); gemm_split_plan makes at most 8 of them, so the loop
-    // unrolls completely and all 8 x 3 loads are in flight together (one L2 round trip)
-    const float4* p4 = reinterpret_cast<const float4*>(upd.ptr + row * d);
+    // K ranges in index order; at most 8 (dec_gemm_split_plan), predicated so that all loads are in flight together
+    const float4* p4 = reinterpret_cast<const float4*>(upd.ptr + row * d) + tid;
     const long st4 = upd.stride >> 2;
-#pragma unroll 8
-    for (int s = 0; s < upd.nsplit; ++s) {
+    float4 q[8];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = i * 128 + tid;
-        if (c < n4) {
-          const float4 p = __ldcg(p4 + s * st4 + c);
-          v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
-        }
-      }
-    }
+    for (int s = 0; s < 8; ++s) q[s] = s < upd.nsplit ? __ldcg(p4 + s * st4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = i * 128 + tid;
-      if (c < n4) x4[c] = v[i];
-    }
+    for (int s = 0; s < 8; ++s) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }
+    *x4 = v;
   }
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  sum = warp_sum(sum);
-  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  float sum = warp_sum((v.x + v.y) + (v.z + v.w));
+  if ((tid & 31) == 0) red[0][tid >> 5] = sum;
   __syncthreads();
-  const float mean = (red[0] + red[1] + red[2] + red[3]) / d;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    if (i * 128 + tid < n4) {
-      const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
-      sq += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
-    }
-  }
-  sq = warp_sum(sq);
-  if ((tid & 31) == 0) red[4 + (tid >> 5)] = sq;
+  sum = warp_sum((tid & 31) < nw ? red[0][tid & 31] : 0.f);   // every warp folds the (<= 12) warp sums itself
+  const float mean = sum / d;
+  const float a = v.x - mean, b2 = v.y - mean, c2 = v.z - mean, d2 = v.w - mean;
+  float sq = warp_sum((a * a + b2 * b2) + (c2 * c2 + d2 * d2));
+  if ((tid & 31) == 0) red[1][tid >> 5] = sq;
   __syncthreads();
-  const float rstd = rsqrtf((red[4] + red[5] + red[6] + red[7]) / d + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  const float4* b4 = reinterpret_cast<const float4*>(be);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int c = i * 128 + tid;
-    if (c < n4) {
-      const float4 gg = g4[c], bb = b4[c];
-      __align__(8) __half2 h[2] = {
-          __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
-          __floats2half2_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w)};
-      *reinterpret_cast<uint2*>(y + row * d + 4 * c) = *reinterpret_cast<const uint2*>(h);
-    }
-  }
+  sq = warp_sum((tid & 31) < nw ? red[1][tid & 31] : 0.f);
+  const float rstd = rsqrtf(sq / d + 1e-5f);
+  __align__(8) __half2 h[2] = {__floats2half2_rn(a * rstd * gg.x + bb.x, b2 * rstd * gg.y + bb.y),
+                               __floats2half2_rn(c2 * rstd * gg.z + bb.z, d2 * rstd * gg.w + bb.w)};
+  *reinterpret_cast<uint2*>(y + row * d + 4 * tid) = *reinterpret_cast<const uint2*>(h);
 }
 
 void layernorm_update_rows(cudaStream_t st, float* x, const PartialSrc& upd, const float* gamma, const float* beta, __half* y,
                            int rows, int d) {
-  WL_CHECK(d <= 1536 && d % 4 == 0, WL_ERR_ARG, "layernorm_update: unsupported width %d", d);
-  WL_CHECK(upd.nsplit == 0 || upd.stride % 4 == 0, WL_ERR_ARG, "layernorm_update: partial stride must be a multiple of 4");
-  launch_kernel(layernorm_update_kernel, dim3(rows), dim3(128), 0, st, x, upd, gamma, beta, y, d);
+  WL_CHECK(d <= 1536 && d % 128 == 0, WL_ERR_ARG, "layernorm_update: unsupported width %d", d);
+  WL_CHECK(upd.nsplit >= 0 && upd.nsplit <= 8 && (upd.nsplit == 0 || upd.stride % 4 == 0), WL_ERR_ARG,
+           "layernorm_update: at most 8 K ranges, stride a multiple of 4");
+  launch_kernel(layernorm_update_kernel, dim3(rows), dim3(d / 4), 0, st, x, upd, gamma, beta, y, d);
   note_launch(1);
 }
 
@@ -209,21 +177,25 @@ void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const f
 }
 
 // ---------------------------------------------------------------------------- gelu_cast
-__global__ void gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int rows, int cols) {
+__global__ void __launch_bounds__(256) gelu_cast_kernel(PartialSrc in, __half* __restrict__ out, int rows, int cols) {
   const long i4 = blockIdx.x * 256L + threadIdx.x;          // float4 index
   const int c4n = cols >> 2;
   pdl_trigger();
   if (i4 >= (long)rows * c4n) return;
-  const int c = (int)(i4 % c4n);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in.bias) v = __ldg(reinterpret_cast<const float4*>(in.bias) + c);
+  if (in.bias) v = __ldg(reinterpret_cast<const float4*>(in.bias) + (int)(i4 % c4n));
   tl_stamp(TL_GELU, 0);
   pdl_wait();
   tl_stamp(TL_GELU, 1);
   const float4* p4 = reinterpret_cast<const float4*>(in.ptr) + i4;
   const long st4 = in.stride >> 2;
-#pragma unroll 4
-  for (int s = 0; s < in.nsplit; ++s) {
+  float4 q[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) q[s] = s < in.nsplit ? __ldcg(p4 + s * st4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { v.x += q[s].x; v.y += q[s].y; v.z += q[s].z; v.w += q[s].w; }
+#pragma unroll 1
+  for (int s = 4; s < in.nsplit; ++s) {   // more than 4 ranges never happens for the 4d-wide FC1 (tiles alone fill the SMs)
     const float4 p = __ldcg(p4 + s * st4);
     v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
   }

@@ -188,6 +188,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     WL_CUDA(cudaEventCreate(&c->ev0));
     WL_CUDA(cudaEventCreate(&c->ev1));
     gemm_prime();
+    dec_gemm_prime();
     attention_prime();
     search_prime();
     flash_attn_prime();
@@ -196,7 +197,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
       WL_CUDA(cudaMalloc((void**)&c->tl_dev, (size_t)(TL_CAP + 1) * 8));
       WL_CUDA(cudaMemset(c->tl_dev, 0, (size_t)(TL_CAP + 1) * 8));
       c->allocs.push_back(c->tl_dev);
-      gemm_tl_bind(c->tl_dev); attention_tl_bind(c->tl_dev); elementwise_tl_bind(c->tl_dev); search_tl_bind(c->tl_dev);
+      gemm_tl_bind(c->tl_dev); dec_gemm_tl_bind(c->tl_dev); attention_tl_bind(c->tl_dev); elementwise_tl_bind(c->tl_dev); search_tl_bind(c->tl_dev);
     }
     c->enc.resize(c->Le);
     c->dec.resize(c->Ld);
@@ -231,7 +232,7 @@ extern "C" void wl_destroy(wl_ctx* c) {
 
 extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
 extern "C" int64_t wl_kernel_launches(wl_ctx* c) {
-  return c ? gemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
+  return c ? gemm_launch_count() + dec_gemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
 }
 extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) {
   if (!c) return -1.f;
@@ -451,6 +452,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
   c->kcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
   c->vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
   c->xws.part = dalloc<float>(c, (size_t)c->Bm * H * 12 * MAX_ROWS_PER_STREAM * 66);
+  c->xws.merge_cnt = dalloc<int>(c, (size_t)c->Bm * H);
   c->xws.probs = nullptr;
   c->post_bar = dalloc<unsigned>(c, 2);
   c->suppress_mask = dalloc<unsigned>(c, (V + 31) / 32 + 1);
@@ -720,17 +722,27 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   static const bool simt_env = [] { const char* e = getenv("WLB200_GEMM_SIMT"); return e && atoi(e) != 0; }();
   const bool fuse = fuse_env && splitk && !simt_env;
   struct Post { int kind = GEMM_POST_NONE; const float* g = nullptr; const float* b = nullptr; };
-  auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias, Post post) -> PartialSrc {
+  auto part_gemm = [&](const __half* W, int n_out, int K, const __half* X, float* buf, const float* bias, Post post,
+                       int max_split = 8) -> PartialSrc {
     GemmEpilogue e;
     e.out = buf; e.out_f32 = 1; e.ldn = n_out; e.ldm = 1;
     e.a_static = 1;
     PartialSrc ps;
     ps.ptr = buf; ps.bias = bias; ps.stride = (long)c->Rm * n_out;
     if (splitk) {
-      ps.nsplit = gemm_split_plan(n_out, R, K);
+      int s2 = std::min(gemm_split_plan(n_out, R, K), max_split);
+      const int total_kb = cdiv(K, 64);
+      while (s2 > 1 && cdiv(total_kb, cdiv(total_kb, s2)) != s2) --s2;   // every K range must be non-empty
+      ps.nsplit = s2;
       e.partials = ps.nsplit; e.part_stride = ps.stride;
     } else {
       ps.nsplit = 1;   // single pass, bias still added by the consumer
+    }
+    static const bool compact = [] { const char* e2 = getenv("WLB200_DEC_GEMM"); return e2 ? atoi(e2) != 0 : true; }();
+    if (compact && splitk && post.kind == GEMM_POST_NONE && !simt_env) {
+      ps.nsplit = dec_gemm_split_plan(n_out, R, K, max_split);
+      dec_gemm(st, W, n_out, K, X, R, buf, n_out, ps.stride, ps.nsplit);
+      return ps;
     }
     if (post.kind != GEMM_POST_NONE) {
       e.post = post.kind;
@@ -753,7 +765,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
                       c->cache_row_stride, c->datt, R, H, d);
     pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o, ln_post(L.ln2_g, L.ln2_b));
     if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
-    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc, Post());
+    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc, Post(), 4);   // cross-attention sums <= 4 ranges
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -782,11 +794,16 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   }
   if (!fuse) layernorm_update_rows(st, c->dx, pending, c->lnf_g, c->lnf_b, c->dxn, R, d);
   {
-    GemmEpilogue e;
-    e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;
-    e.ldm = 1;
-    e.a_static = 1;
-    gemm_tn(st, opnd(c->emb, c->V, d, d), opnd(c->dxn, R, d, d), c->V, R, d, e);
+    static const bool compact = [] { const char* e2 = getenv("WLB200_DEC_GEMM"); return e2 ? atoi(e2) != 0 : true; }();
+    if (compact && !simt_env) {
+      dec_gemm(st, c->emb, c->V, d, c->dxn, R, c->logits, c->Vld, 0, 1);
+    } else {
+      GemmEpilogue e;
+      e.out = c->logits; e.out_f32 = 1; e.ldn = c->Vld;
+      e.ldm = 1;
+      e.a_static = 1;
+      gemm_tn(st, opnd(c->emb, c->V, d, d), opnd(c->dxn, R, d, d), c->V, R, d, e);
+    }
   }
   search_rows(st, s, c->logits, so, vi, R);
   search_streams(st, s, so, vi, B);
@@ -917,7 +934,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
              so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
-      const long before = gemm_launch_count() + other_launch_count();
+      const long before = gemm_launch_count() + dec_gemm_launch_count() + other_launch_count();
       cudaGraph_t g = nullptr, cap = nullptr;
       if (loop_graph) {
         WL_CUDA(cudaGraphCreate(&g, 0));
@@ -950,7 +967,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
         }
         WL_CUDA(cudaStreamEndCapture(st, &g));
       }
-      ge.kernels = gemm_launch_count() + other_launch_count() - before;
+      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + other_launch_count() - before;
       c->capture_counted += ge.kernels;
       WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
       cudaGraphDestroy(g);
@@ -1247,6 +1264,9 @@ extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_
     WL_CUDA(cudaMalloc((void**)&dbias, (size_t)std::max(M, N) * 4));
     WL_CUDA(cudaMemcpy(dbias, bias, (size_t)(transposed_store ? M : N) * 4, cudaMemcpyHostToDevice));
   }
+  // the copies / memset above ran on the legacy default stream, the GEMM runs on the library's non-blocking stream:
+  // without this the kernel may overtake the memset of its own output buffer
+  WL_CUDA(cudaDeviceSynchronize());
   GemmEpilogue e;
   e.out = dc; e.out_f32 = 1; e.gelu = gelu; e.bias = dbias;
   if (transposed_store) { e.ldm = 1; e.ldn = M; e.bias_on_m = 1; }   // C^T stored: [N][M]
@@ -1284,6 +1304,7 @@ extern "C" int wl_bench_gemm(wl_ctx* c, int32_t M, int32_t N, int32_t K, int32_t
   WL_CUDA(cudaMemset(db, 0x11, nb * 2));
   WL_CUDA(cudaMemset(dc, 0, nc * (f32 ? 4 : 2)));
   WL_CUDA(cudaMemset(dbias, 0, (size_t)std::max(M, N) * 4));
+  WL_CUDA(cudaDeviceSynchronize());
   GemmEpilogue e;
   e.out = dc; e.out_f32 = f32 ? 1 : 0;
   if (tr) { e.ldm = 1; e.ldn = M; } else { e.ldm = N; e.ldn = 1; }

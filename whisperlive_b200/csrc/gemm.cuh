@@ -69,6 +69,15 @@ void gemm_tn_simt(cudaStream_t stream, const GemmOperand& A, const GemmOperand& 
 long gemm_launch_count();
 int gemm_split_plan(int M, int N, int K);
 
+// Compact decode-step GEMM (dec_gemm.cu): out[s][r][ldn] (s < nsplit) = partial sums over K range s of
+// W[n_out, K] x X[R, K]^T, fp32, no bias.  nsplit from dec_gemm_split_plan (1 for the vocabulary projection).
+void dec_gemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, int R, float* out, int ldn, long part_stride,
+              int nsplit);
+int dec_gemm_split_plan(int n_out, int R, int K, int max_split = 8);
+long dec_gemm_launch_count();
+void dec_gemm_prime();
+void dec_gemm_tl_bind(unsigned long long* p);
+
 // Tensor map over an operand view (dims sorted by stride) + the coordinate slots of (row, i1, i2).
 struct TmapInfo {
   CUtensorMap tm;
