@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="chunk length of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the in-run CPU baseline")
+    ap.add_argument("--word-timestamps", action="store_true", help="BASELINE config 4: K14 word alignment on every chunk (e2e only)")
     return ap.parse_args()
 
 
@@ -117,6 +119,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def physical_cores():
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False)
+    except Exception:
+        return None
+
+
 def cpu_oracle_sample(model: str, beam: int, seconds: float, threads: int):
     """The CPU arm: oracle port (torch fp32 + restated CT2 search) on one bounded chunk."""
     import torch
@@ -161,7 +171,8 @@ def run_reference(args, rank: int, world: int):
         "config": {"workload": f"Whisper {args.model} random-init, CPU sample of the bench workload", "beam": args.beam,
                    "sample": sample},
         "p50_chunk_latency_ms": 1000 * statistics.median(times),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "physical_cores": physical_cores(),
+                         "logical_cpus": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,11 +215,15 @@ def main():
                              feature_extractor=FeatureExtractor(eng, dims.n_mels))
     tok_eot = eng.eot
     n_sot = 3 if dims.multilingual else 1   # CT2 decodes min(max_length/2, max_length - prompt) tokens: 2N gives N
-    kws = [dict(beam_size=args.beam, temperature=[0.0], log_prob_threshold=None, compression_ratio_threshold=None,
-                no_speech_threshold=None, suppress_tokens=[-1, tok_eot], suppress_blank=False,
-                max_new_tokens=2 * tokens_for(d) - n_sot, language="en" if dims.multilingual else None,
-                condition_on_previous_text=False, _single_window=True) for d in my_durs]
+    all_kws = [dict(beam_size=args.beam, temperature=[0.0], log_prob_threshold=None, compression_ratio_threshold=None,
+                    no_speech_threshold=None, suppress_tokens=[-1, tok_eot], suppress_blank=False,
+                    max_new_tokens=2 * tokens_for(d) - n_sot, language="en" if dims.multilingual else None,
+                    condition_on_previous_text=False, word_timestamps=bool(args.word_timestamps), _single_window=True)
+               for d in durs]
     audio_sec_total = float(sum(durs))
+    # the product's multi-GPU front end: streams placed i mod W, one all-gather of ids + times per batch
+    from whisperlive_b200.parallel import DistributedTranscriber
+    dist_tr = DistributedTranscriber(model)
 
     def barrier():
         if world > 1:
@@ -217,16 +232,9 @@ def main():
 
     def e2e_step():
         t0 = time.perf_counter()
-        out = model.transcribe_batch(my_waves, kws)
-        ids = [t for segs, _ in out for s in (segs or []) for t in s.tokens]
-        if world > 1:  # every rank ends up with the whole batch's token ids (one collective per batch)
-            mx = torch.tensor([len(ids)], device="cuda")
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            buf = torch.full((int(mx.item()) + 1,), -1, dtype=torch.int32, device="cuda")
-            buf[:len(ids)] = torch.tensor(ids, dtype=torch.int32, device="cuda")
-            gathered = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(gathered, buf)
-        return time.perf_counter() - t0, len(ids)
+        out = dist_tr.transcribe_batch(waves, all_kws)      # whole batch in, whole batch out on every rank
+        n_ids = sum(len(s.tokens) for segs, _ in out for s in (segs or []))
+        return time.perf_counter() - t0, n_ids
 
     # ---- resident-input step: PCM / features already in HBM, device-timed
     feats_cache = {}
@@ -311,10 +319,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 32)
         step, seconds, n_new = cpu_oracle_sample(args.model, args.beam, args.cpu_seconds, threads)
-        dt = step()
-        cpu = {"value": seconds / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"1 stream x {seconds:.0f} s chunk, {n_new} decoded tokens, beam {args.beam}, torch fp32 oracle port "
-                         f"(stand-in, not the reference binary: faster-whisper/CTranslate2 absent), {dt:.1f} s wall"}
+        step()                                               # warm-up (thread pool, allocator)
+        cts = [step() for _ in range(max(1, args.cpu_steps))]
+        cpu = {"value": seconds * len(cts) / sum(cts), "unit": UNIT, "cores": threads, "physical_cores": physical_cores(),
+               "logical_cpus": os.cpu_count(), "kind": "port", "steps": len(cts), "step_s": [round(x, 2) for x in cts],
+               "sample": f"{len(cts)} timed steps after 1 warm-up, each 1 stream x {seconds:.0f} s chunk, {n_new} decoded tokens, beam "
+                         f"{args.beam}, torch fp32 oracle port on {threads} threads (stand-in, not the reference binary: "
+                         f"faster-whisper/CTranslate2 absent)"}
     if rank == 0:
         line = {
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -327,7 +338,9 @@ def main():
                        "l2": "working set (3.1 GB weights + 246 MB/stream cross-KV) >> 126 MB L2, no flush needed"},
             "p50_chunk_latency_ms": 1000 * statistics.median(lat),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1000 * t_e2e / args.steps, "api": "B200WhisperModel.transcribe_batch(host PCM)"},
+                    "ms_per_step": 1000 * t_e2e / args.steps,
+                    "api": "whisperlive_b200.parallel.DistributedTranscriber(B200WhisperModel).transcribe_batch(host PCM)",
+                    "gather_bytes_per_step": int(dist_tr.last_gather_bytes), "word_timestamps": bool(args.word_timestamps)},
             "gpu_launches": int(launches_res),
             "clocks": clocks,
             "roofline": roof,

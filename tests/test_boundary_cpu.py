@@ -164,36 +164,30 @@ import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 from tests.test_boundary_cpu import _oracle_model
 from whisperlive_b200 import synth
+from whisperlive_b200.parallel import DistributedTranscriber
 torch.set_num_threads(2)
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
-rank, world = dist.get_rank(), dist.get_world_size()
 n_streams = 3
 waves = [synth.speech_like(2.0 + i, seed=40 + i) for i in range(n_streams)]
-mine = [i for i in range(n_streams) if i % world == rank]
-model = _oracle_model()
 kw = dict(temperature=[0.0], beam_size=2, log_prob_threshold=None, max_new_tokens=16)
-out = model.transcribe_batch([waves[i] for i in mine], [kw] * len(mine))
-ids = [[t for s in segs for t in s.tokens] for segs, _ in out]
-flat = torch.full((n_streams, 64), -1, dtype=torch.int32)
-for i, seq in zip(mine, ids):
-    flat[i, :len(seq)] = torch.tensor(seq, dtype=torch.int32)
-gathered = [torch.empty_like(flat) for _ in range(world)]
-dist.all_gather(gathered, flat)            # one collective per batch: emitted token ids
-merged = torch.stack(gathered).max(0).values
-if rank == 0:
-    print("RESULT " + json.dumps(merged.tolist()))
+dt = DistributedTranscriber(_oracle_model())          # the product API: shards by rank, gathers ids + times
+out = dt.transcribe_batch(waves, [kw] * n_streams)      # every rank passes (and gets back) the whole batch
+res = [[[s.tokens, round(s.start, 3), round(s.end, 3)] for s in segs] for segs, _ in out]
+owned = dt.owned(n_streams)
+print("RESULT%d " % dist.get_rank() + json.dumps({"res": res, "owned": owned, "bytes": dt.last_gather_bytes}))
 dist.destroy_process_group()
 """
 
 
 def test_two_rank_stream_sharding_matches_single_process(tmp_path):
-    """world_size=2 (gloo): streams sharded round-robin, token ids all-gathered; equals 1-process output."""
+    """world_size=2 (gloo) through whisperlive_b200.parallel.DistributedTranscriber: streams sharded i mod W, one
+    all-gather of ids + times per batch; BOTH ranks end up with the single-process result for every stream."""
     from whisperlive_b200 import synth
     torch.set_num_threads(4)
     model = _oracle_model()
     kw = dict(temperature=[0.0], beam_size=2, log_prob_threshold=None, max_new_tokens=16)
     waves = [synth.speech_like(2.0 + i, seed=40 + i) for i in range(3)]
-    single = [[t for s in segs for t in s.tokens] for segs, _ in model.transcribe_batch(waves, [kw] * 3)]
+    single = [[[s.tokens, round(s.start, 3), round(s.end, 3)] for s in segs] for segs, _ in model.transcribe_batch(waves, [kw] * 3)]
     script = tmp_path / "w.py"
     script.write_text(GLOO_WORKER)
     port = str(29500 + os.getpid() % 2000)
@@ -201,10 +195,40 @@ def test_two_rank_stream_sharding_matches_single_process(tmp_path):
                               text=True) for r in range(2)]
     outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    line = next(l for l in outs[0][0].splitlines() if l.startswith("RESULT "))
-    merged = json.loads(line[len("RESULT "):])
-    for i, seq in enumerate(single):
-        assert [t for t in merged[i] if t >= 0] == seq
+    for r in range(2):
+        line = next(l for l in outs[r][0].splitlines() if l.startswith(f"RESULT{r} "))
+        got = json.loads(line[len(f"RESULT{r} "):])
+        assert got["owned"] == [i for i in range(3) if i % 2 == r] and got["bytes"] > 0
+        assert got["res"] == single, (r, got["res"], single)
+
+
+def test_multi_device_model_fans_out_and_keeps_order():
+    """One process, several engine contexts (MultiDeviceWhisperModel): sticky i mod G placement, results in input order,
+    explicit placement honoured, a failing device propagates its error."""
+    from whisperlive_b200.parallel import MultiDeviceWhisperModel, owner_of
+
+    class Fake:
+        def __init__(self, g):
+            self.g, self.calls = g, []
+            self.model = self
+            self.hf_tokenizer = None
+
+        def transcribe_batch(self, audios, kws):
+            self.calls.append([len(a) for a in audios])
+            if any(len(a) == 13 for a in audios):
+                raise RuntimeError("boom")
+            return [((self.g, len(a)), k.get("tag")) for a, k in zip(audios, kws)]
+    fakes = [Fake(0), Fake(1), Fake(2)]
+    m = MultiDeviceWhisperModel(models=fakes, device_index=[0, 1, 2])
+    audios = [np.zeros(n, np.float32) for n in (5, 6, 7, 8, 9)]
+    out = m.transcribe_batch(audios, [dict(tag=i) for i in range(5)])
+    assert out == [((owner_of(i, 3), 5 + i), i) for i in range(5)]
+    assert fakes[0].calls == [[5, 8]] and fakes[1].calls == [[6, 9]] and fakes[2].calls == [[7]]
+    out = m.transcribe_batch(audios[:2], None, placement=[2, 2])
+    assert [o[0][0] for o in out] == [2, 2]
+    with pytest.raises(RuntimeError):
+        m.transcribe_batch([np.zeros(13, np.float32)], None)
+    m.close()
 
 
 def test_bench_reference_arm_prints_the_contract_line():

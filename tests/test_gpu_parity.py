@@ -634,10 +634,10 @@ def test_transcribe_batch_more_streams_than_slots():
     eng = B200Whisper(dims, random_init(dims, seed=0), max_streams=2, max_beam=5)
     m = B200WhisperModel("micro.en", engine=eng, hf_tokenizer="synthetic", feature_extractor=FeatureExtractor(eng, dims.n_mels))
     audios = [synth.speech_like(33.0 if i % 2 else 6.0, seed=40 + i) for i in range(5)]
-    kw = dict(temperature=[0.0, 0.4], beam_size=5)
+    kw = dict(temperature=[0.0], beam_size=5, log_prob_threshold=None, compression_ratio_threshold=None)
     out = m.transcribe_batch(audios, [kw] * 5)
     assert len(out) == 5 and all(segs is not None and len(segs) > 0 for segs, _ in out)
-    solo = m.transcribe(audios[3], **kw)
+    solo = m.transcribe(audios[3], **kw)      # no sampling rungs: batched and solo runs are comparable token for token
     assert [s.tokens for s in solo[0]] == [s.tokens for s in out[3][0]]
     gc.collect()
     assert eng.free_slots() == eng.enc_slots

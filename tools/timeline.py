@@ -31,7 +31,12 @@ def main(path):
         (t0, k0), (t1, k1) = ready[i], ready[i + 1]
         name = NAMES.get(k0, str(k0))
         if k0 == 3:
-            name += {4: " qkv", 5: " q_cross", 7: " fc1"}.get(k1, " out/fc2 (->LN)")
+            if k1 == 3:
+                name += " (cold launch, WLB200_DUP)"
+            else:
+                name += {4: " qkv", 5: " q_cross", 7: " fc1", 8: " vocab"}.get(k1, " out/fc2 (->LN)")
+                if i > 0 and ready[i - 1][1] == 3:
+                    name += " [warm repeat]"
         iv[name].append((t1 - t0) / 1e3)
     tot = sum(sum(v) for v in iv.values())
     print(f"{'kernel':32s} {'n':>7s} {'mean us':>9s} {'p50':>8s} {'p90':>8s} {'share':>7s}")
@@ -47,8 +52,11 @@ def main(path):
         elif k in ent:
             ahead[NAMES.get(k, str(k))].append((tt - ent.pop(k)) / 1e3)
     print("\nentry -> ready (resident ahead of its dependency):")
-    for name, v in ahead.items():
-        print(f"  {name:28s} mean {np.mean(v):6.2f} us")
+    try:
+        for name, v in ahead.items():
+            print(f"  {name:28s} mean {np.mean(v):6.2f} us")
+    except BrokenPipeError:
+        pass
 
 
 if __name__ == "__main__":

@@ -77,9 +77,14 @@ if ServeClientBase is not None:
             """Build the shared transcriber (CUDA engine). Raises when no B200 / library is available."""
             if ServeClientB200.MODEL_FACTORY is not None:
                 return ServeClientB200.MODEL_FACTORY(self.model_size_or_path)
+            from .parallel import MultiDeviceWhisperModel, devices_from_env
             from .transcriber import B200WhisperModel
-            return B200WhisperModel(self.model_size_or_path, device="cuda", compute_type=self.compute_type,
-                                    max_streams=ServeClientB200.MAX_STREAMS)
+            devices = devices_from_env()     # WLB200_DEVICES=0,1,...: one engine context per GPU, streams placed i mod G
+            if len(devices) > 1:
+                return MultiDeviceWhisperModel(self.model_size_or_path, device_index=devices, device="cuda",
+                                               compute_type=self.compute_type, max_streams=ServeClientB200.MAX_STREAMS)
+            return B200WhisperModel(self.model_size_or_path, device="cuda", device_index=devices[0],
+                                    compute_type=self.compute_type, max_streams=ServeClientB200.MAX_STREAMS)
 
         def set_language(self, info):
             if info.language_probability > 0.5:

@@ -3,7 +3,7 @@
 //       (row, head), CUDA-core math (a few KB of work per warp).
 //   K11 decoder_cross_attn: all rows (beams) of a stream against the stream's persistent encoder K/V -- persistent
 //       CTAs, K/V streamed HBM -> smem by a producer warp (cp.async.bulk + mbarrier ring), consumed by 4 warps with
-//       mma.sync on the pre-swizzled chunks; partial softmaxes per key range merged by the last range to finish.
+//       mma.sync on the pre-swizzled chunks; partial softmaxes per key range merged by a small combine kernel.
 //   Reference call site of both: ctranslate2 Whisper.generate, transcriber_faster_whisper.py:1394-1407.
 #include <algorithm>
 #include <cstdlib>
@@ -210,7 +210,7 @@ template <int NQ> struct XaCfg {
 template <int NQ, int XA_STAGES>
 __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialSrc q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
-                                                         long slot_stride, float* __restrict__ part, int* __restrict__ merge_cnt,
+                                                         long slot_stride, float* __restrict__ part,
                                                          float* __restrict__ probs, __half* __restrict__ out, int B,
                                                          int rows_per_stream, int H, int d, int nsplit, int cps, int dbg) {
   constexpr int SW = XaCfg<NQ>::SW;
@@ -232,7 +232,6 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ uint8_t live[MAX_STREAMS_CAP];
   __shared__ int n_live_sh;
-  __shared__ int xa_last;
   pdl_trigger();
 
   if (tid == 0) {
@@ -535,35 +534,45 @@ __global__ void __launch_bounds__(160) cross_attn_kernel(DecodeState s, PartialS
     dst[tid * 66 + 0] = mx[tid];
     dst[tid * 66 + 1] = sm[tid];
   }
-  // The LAST key range of this (stream, head) to get here merges all nsplit partial softmaxes -- always in key-range
-  // order, so the result does not depend on who arrives last -- and writes the attention output.  Round 1 ran this
-  // merge as a separate kernel (cross_attn_combine: one more stage on the per-layer dependency chain).
-  __threadfence();
-  consumers_sync();   // every partial of this CTA is visible device-wide; ored may be rewritten from here on
-  if (tid == 0) {
-    const int prev = atomicAdd(merge_cnt + b * H + h, 1);
-    xa_last = prev == nsplit - 1;
-    if (xa_last) merge_cnt[b * H + h] = 0;   // ready for the next launch (next layer): nobody else touches it any more
-  }
-  consumers_sync();
-  if (xa_last) {
-    __threadfence();
-    for (int idx = tid; idx < rows_per_stream * 64; idx += 128) {
-      const int j = idx >> 6, dd = idx & 63;
-      const float* p = pbase + j * 66;
-      float M = -INFINITY;
-      for (int q2 = 0; q2 < nsplit; ++q2) M = fmaxf(M, __ldcg(p + (long)q2 * MAX_ROWS_PER_STREAM * 66));
-      float L = 0.f, o2 = 0.f;
-      for (int q2 = 0; q2 < nsplit; ++q2) {
-        const float* ps = p + (long)q2 * MAX_ROWS_PER_STREAM * 66;
-        const float w = __expf(__ldcg(ps) - M);
-        L += __ldcg(ps + 1) * w;
-        o2 += __ldcg(ps + 2 + dd) * w;
-      }
-      out[(long)(row0 + j) * d + h * 64 + dd] = __float2half_rn(o2 / L);
-    }
-  }
+  consumers_sync();   // ored is rewritten by the next item
   }   // item loop
+}
+
+// Merge the nsplit partial softmaxes of every (row, head), in key-range order.  A separate (tiny) kernel on purpose:
+// merging inside cross_attn_kernel (last key range to arrive, found with a fence + atomic) was measured at the same
+// cost at 4 streams and 5 us WORSE at 32 streams, where every persistent CTA pays the fence/atomic round trip once per
+// item in the middle of its K/V stream (in-graph timeline, profiles/timeline_r2.md).
+__global__ void __launch_bounds__(64) cross_attn_combine_kernel(DecodeState s, const float* __restrict__ part, __half* __restrict__ out,
+                                                                int rows_per_stream, int H, int d, int nsplit) {
+  const int r = blockIdx.y, h = blockIdx.x, dd = threadIdx.x;
+  const int b = r / rows_per_stream, j = r - b * rows_per_stream;
+  pdl_trigger();
+  if (s.done[b]) return;
+  tl_stamp(TL_COMBINE, 0);
+  pdl_wait();
+  tl_stamp(TL_COMBINE, 1);
+  const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
+  // all loads first (independent, one L2 round trip), then the arithmetic; nsplit <= 12
+  float m[XA_NCHUNK], l[XA_NCHUNK], o[XA_NCHUNK];
+#pragma unroll
+  for (int sp = 0; sp < XA_NCHUNK; ++sp) {
+    const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
+    const bool on = sp < nsplit;
+    m[sp] = on ? __ldcg(ps) : -INFINITY;
+    l[sp] = on ? __ldcg(ps + 1) : 0.f;
+    o[sp] = on ? __ldcg(ps + 2 + dd) : 0.f;
+  }
+  float M = -INFINITY;
+#pragma unroll
+  for (int sp = 0; sp < XA_NCHUNK; ++sp) M = fmaxf(M, m[sp]);
+  float L = 0.f, acc = 0.f;
+#pragma unroll
+  for (int sp = 0; sp < XA_NCHUNK; ++sp) {
+    const float w = sp < nsplit ? __expf(m[sp] - M) : 0.f;
+    L += l[sp] * w;
+    acc += o[sp] * w;
+  }
+  out[(long)r * d + h * 64 + dd] = __float2half_rn(acc / L);
 }
 
 static int xa_template_nq(int rows_per_stream) {
@@ -648,7 +657,7 @@ static void launch_cross(cudaStream_t st, const DecodeState& s, const PartialSrc
   const int stg = xa_stages();
   auto k = stg == 2 ? cross_attn_kernel<NQ, 2> : stg == 4 ? cross_attn_kernel<NQ, 4> : cross_attn_kernel<NQ, 3>;
   if (ws.ev0) WL_CUDA(cudaEventRecord(ws.ev0, st));
-  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.merge_cnt, ws.probs, out, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
+  launch_kernel(k, grid, dim3(160), (size_t)smem, st, s, q, kc, vc, slot_stride, ws.part, ws.probs, out, B, rows_per_stream, H, d, nsplit, cps, xa_dbg());
   if (ws.ev1) WL_CUDA(cudaEventRecord(ws.ev1, st));
   note_launch(1);
 }
@@ -678,6 +687,10 @@ void decoder_cross_attn(cudaStream_t st, const DecodeState& s, const PartialSrc&
   else if (rows_per_stream <= 4) launch_cross<4>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else if (rows_per_stream == 5) launch_cross<5>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
   else launch_cross<8>(st, s, q, kc, vc, slot_stride, ws, out, B, rows_per_stream, H, d, nsplit);
+  if (nsplit > 1) {
+    launch_kernel(cross_attn_combine_kernel, dim3(H, B * rows_per_stream), dim3(64), 0, st, s, ws.part, out, rows_per_stream, H, d, nsplit);
+    note_launch(1);
+  }
 }
 
 }  // namespace wl

@@ -174,11 +174,13 @@ static void dg_prime() {
   WL_CUDA(cudaFuncSetAttribute(dec_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem<BN, STAGES>()));
 }
 void dec_gemm_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
+// Ring depth = how many weight k-blocks are in flight BEFORE the dependency wait resolves (PDL): 8 stages cover a whole
+// K range of every decode GEMM but FC2 (10 k-blocks), so the weights are in shared memory when X arrives.
 void dec_gemm_prime() {
-  dg_prime<16, 4>();
-  dg_prime<32, 4>();
-  dg_prime<64, 4>();
-  dg_prime<128, 4>();
+  dg_prime<16, 8>();
+  dg_prime<32, 8>();
+  dg_prime<64, 6>();
+  dg_prime<128, 6>();
 }
 
 static int dg_bn(int R) { return R <= 16 ? 16 : R <= 32 ? 32 : R <= 64 ? 64 : 128; }
@@ -214,10 +216,10 @@ void dec_gemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* 
   p.nsplit = nsplit;
   const int grid = p.tiles_m * nsplit * cdiv(R, bn);
   switch (bn) {
-    case 16: dg_launch<16, 4>(st, ia.tm, ib.tm, p, grid); break;
-    case 32: dg_launch<32, 4>(st, ia.tm, ib.tm, p, grid); break;
-    case 64: dg_launch<64, 4>(st, ia.tm, ib.tm, p, grid); break;
-    default: dg_launch<128, 4>(st, ia.tm, ib.tm, p, grid); break;
+    case 16: dg_launch<16, 8>(st, ia.tm, ib.tm, p, grid); break;
+    case 32: dg_launch<32, 8>(st, ia.tm, ib.tm, p, grid); break;
+    case 64: dg_launch<64, 6>(st, ia.tm, ib.tm, p, grid); break;
+    default: dg_launch<128, 6>(st, ia.tm, ib.tm, p, grid); break;
   }
   g_dec_gemm_launches++;
 }

@@ -119,7 +119,6 @@ void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& 
 //   q f32 [R][d]; K/V caches [slot][H][1500][64] fp16 (layer base pointers); out fp16 [R][d]
 struct CrossAttnWorkspace {
   float* part;     // [B][H][nsplit][MAX_ROWS_PER_STREAM][66]  (m, l, o[64])
-  int* merge_cnt;  // [B][H] arrival counters of the key ranges (zero between launches)
   float* probs;    // optional [R][H][1500] f32 attention probabilities (align mode) or nullptr
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // profiling: recorded right before / after the main kernel when set
 };
