@@ -112,6 +112,11 @@ int wl_decode_logits(wl_ctx* ctx, const int32_t* slots, int32_t B, const int32_t
 /* C[z] = A[z] (MxK) * B[z]^T (NxK) (+bias[n]) on the tcgen05 path (use_simt=0) or the CUDA-core checker */
 int wl_test_gemm(wl_ctx* ctx, const uint16_t* a_f16, const uint16_t* b_f16, const float* bias, float* c, int32_t M, int32_t N,
                  int32_t K, int32_t batch, int32_t transposed_store, int32_t gelu, int32_t use_simt);
+/* test hook of the small-batch decode GEMM (csrc/wgemm.cu, R <= 32): out[R][n_out] = X[R][K] W[n_out][K]^T with the fused
+ * epilogue `mode` -- 0: + bias; 1: out += acc + bias (residual in place); 2: gelu(acc + bias) through fp16;
+ * 3: split-K partial sums (K > 1280), summed by the hook */
+int wl_test_wgemm(wl_ctx* ctx, const uint16_t* w_f16, const uint16_t* x_f16, const float* bias, float* out, int32_t R,
+                  int32_t n_out, int32_t K, int32_t mode);
 /* device-resident timing of the GEMM kernel: C = A(MxK) * B(NxK)^T, `iters` launches between CUDA events;
  * bn = 0 picks the tile like the engine does. ms_out = average milliseconds per launch. */
 int wl_bench_gemm(wl_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t iters, int32_t flags,

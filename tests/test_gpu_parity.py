@@ -88,6 +88,37 @@ def test_gemm_tcgen05(case):
     np.testing.assert_allclose(tc, ref, atol=2e-3 * np.sqrt(K), rtol=1e-3)
 
 
+WGEMM_CASES = [
+    # (R, n_out, K, mode)   mode 0 bias, 1 residual in place, 2 gelu -> fp16, 3 split-K partials (K > 1280)
+    (16, 1280, 1280, 0), (5, 384, 384, 0), (1, 768, 768, 0), (16, 3840, 1280, 0), (20, 1280, 1280, 1), (32, 128, 128, 1),
+    (16, 5120, 1280, 2), (16, 1280, 5120, 3), (12, 768, 3072, 3), (3, 128, 512, 1), (16, 51200, 1280, 0), (9, 1536, 384, 2),
+]
+
+
+@pytest.mark.parametrize("case", WGEMM_CASES)
+def test_wgemm_small_batch(case):
+    """The small-batch decode GEMM (csrc/wgemm.cu: mma.sync, bulk-copied weight slices, fused epilogues) against fp32
+    numpy on the same fp16 inputs, all four epilogues, ragged row counts, every K the Whisper sizes produce."""
+    eng, _ = engine("micro.en")
+    R, n_out, K, mode = case
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31))
+    w = (rng.standard_normal((n_out, K)) / np.sqrt(K)).astype(np.float16)
+    x = rng.standard_normal((R, K)).astype(np.float16)
+    bias = rng.standard_normal(n_out).astype(np.float32) if mode != 3 else None
+    resid = rng.standard_normal((R, n_out)).astype(np.float32) if mode == 1 else None
+    ref = x.astype(np.float32) @ w.astype(np.float32).T
+    if bias is not None:
+        ref = ref + bias[None, :]
+    if mode == 1:
+        ref = ref + resid
+    if mode == 2:
+        ref = torch.nn.functional.gelu(torch.from_numpy(ref)).numpy()
+    got = eng.test_wgemm(w, x, bias, mode=mode, resid=resid)
+    err = np.abs(got - ref).max()
+    print(f"wgemm {case}: max err {err:.3e}")
+    np.testing.assert_allclose(got, ref, atol=2e-3 if mode != 2 else 4e-3, rtol=2e-3)
+
+
 # --------------------------------------------------------------------------------------- K1 mel
 @pytest.mark.parametrize("n_mels_model", ["micro.en", "large-v3-mel"])
 def test_mel_matches_oracle(n_mels_model):

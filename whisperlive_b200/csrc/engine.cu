@@ -189,6 +189,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     WL_CUDA(cudaEventCreate(&c->ev1));
     gemm_prime();
     dec_gemm_prime();
+    wgemm_prime();
     attention_prime();
     search_prime();
     flash_attn_prime();
@@ -197,7 +198,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
       WL_CUDA(cudaMalloc((void**)&c->tl_dev, (size_t)(TL_CAP + 1) * 8));
       WL_CUDA(cudaMemset(c->tl_dev, 0, (size_t)(TL_CAP + 1) * 8));
       c->allocs.push_back(c->tl_dev);
-      gemm_tl_bind(c->tl_dev); dec_gemm_tl_bind(c->tl_dev); attention_tl_bind(c->tl_dev); elementwise_tl_bind(c->tl_dev); search_tl_bind(c->tl_dev);
+      gemm_tl_bind(c->tl_dev); dec_gemm_tl_bind(c->tl_dev); wgemm_tl_bind(c->tl_dev); attention_tl_bind(c->tl_dev); elementwise_tl_bind(c->tl_dev); search_tl_bind(c->tl_dev);
     }
     c->enc.resize(c->Le);
     c->dec.resize(c->Ld);
@@ -232,7 +233,7 @@ extern "C" void wl_destroy(wl_ctx* c) {
 
 extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
 extern "C" int64_t wl_kernel_launches(wl_ctx* c) {
-  return c ? gemm_launch_count() + dec_gemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
+  return c ? gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
 }
 extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) {
   if (!c) return -1.f;
@@ -759,16 +760,7 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   };
   auto ln_post = [&](const float* g, const float* b) { Post p; if (fuse) { p.kind = GEMM_POST_LN; p.g = g; p.b = b; } return p; };
   PartialSrc pending;   // residual update not yet folded into x (unfused path)
-  for (int l = 0; l < c->Ld; ++l) {
-    const DecLayer& L = c->dec[l];
-    const bool last = l + 1 == c->Ld;
-    if (!fuse || l == 0) layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
-    const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv, Post());
-    decoder_self_attn(st, s, qkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
-                      c->cache_row_stride, c->datt, R, H, d);
-    pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o, ln_post(L.ln2_g, L.ln2_b));
-    if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
-    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc, Post(), 4);   // cross-attention sums <= 4 ranges
+  auto cross = [&](int l, const PartialSrc& qc) {
     CrossAttnWorkspace ws = c->xws;
     ws.probs = align_mode ? c->align_probs : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -785,6 +777,46 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     }
     if (align_mode)
       gather_align_probs(st, s, c->align_probs, c->align_buf, c->align_heads_dev, (int)c->align_heads.size() / 2, l, B, Kr, H);
+  };
+  // Small batches (R <= 32 decoder rows, e.g. 4-8 streams per GPU with beam 4): every linear layer is one wgemm launch
+  // whose epilogue writes FINAL values (bias, residual, GELU fused), so LayerNorm / attention read one value instead of
+  // summing partials and the GELU-cast launch is gone: 12 launches per layer instead of 13, each a fraction of the code.
+  static const bool wg_env = [] { const char* e = getenv("WLB200_WGEMM"); return e ? atoi(e) != 0 : true; }();
+  const bool small = wg_env && !simt_env && !fuse && wgemm_supported(R, d) && wgemm_supported(R, ff);
+  auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
+  for (int l = 0; small && l < c->Ld; ++l) {
+    const DecLayer& L = c->dec[l];
+    layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    wgemm(st, L.w_qkv, 3 * d, d, c->dxn, R, L.b_qkv, 0, c->part1, nullptr, 0);
+    decoder_self_attn(st, s, plain(c->part1), c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
+                      c->cache_row_stride, c->datt, R, H, d);
+    wgemm(st, L.w_o, d, d, c->datt, R, L.b_o, 1, c->dx, nullptr, 0);
+    layernorm_update_rows(st, c->dx, PartialSrc(), L.ln2_g, L.ln2_b, c->dxn, R, d);
+    wgemm(st, L.w_qc, d, d, c->dxn, R, L.b_qc, 0, c->part1, nullptr, 0);
+    cross(l, plain(c->part1));
+    wgemm(st, L.w_oc, d, d, c->datt, R, L.b_oc, 1, c->dx, nullptr, 0);
+    layernorm_update_rows(st, c->dx, PartialSrc(), L.ln3_g, L.ln3_b, c->dxn, R, d);
+    wgemm(st, L.w_fc1, ff, d, c->dxn, R, L.b_fc1, 2, nullptr, c->dh, 0);
+    const int ks2 = wgemm_ksplit(ff);
+    if (ks2 == 1) {
+      wgemm(st, L.w_fc2, d, ff, c->dh, R, L.b_fc2, 1, c->dx, nullptr, 0);
+      pending = PartialSrc();
+    } else {   // K = 4d is split over CTAs: the next LayerNorm folds the ranges (+ bias) into x
+      wgemm(st, L.w_fc2, d, ff, c->dh, R, nullptr, 3, c->part2, nullptr, (long)c->Rm * d);
+      pending.ptr = c->part2; pending.nsplit = ks2; pending.stride = (long)c->Rm * d; pending.bias = L.b_fc2;
+    }
+  }
+  for (int l = 0; !small && l < c->Ld; ++l) {
+    const DecLayer& L = c->dec[l];
+    const bool last = l + 1 == c->Ld;
+    if (!fuse || l == 0) layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv, Post());
+    decoder_self_attn(st, s, qkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
+                      c->cache_row_stride, c->datt, R, H, d);
+    pending = part_gemm(L.w_o, d, d, c->datt, c->part2, L.b_o, ln_post(L.ln2_g, L.ln2_b));
+    if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln2_g, L.ln2_b, c->dxn, R, d);
+    const PartialSrc qc = part_gemm(L.w_qc, d, d, c->dxn, c->part1, L.b_qc, Post(), 4);   // cross-attention sums <= 4 ranges
+    cross(l, qc);
     pending = part_gemm(L.w_oc, d, d, c->datt, c->part2, L.b_oc, ln_post(L.ln3_g, L.ln3_b));
     if (!fuse) layernorm_update_rows(st, c->dx, pending, L.ln3_g, L.ln3_b, c->dxn, R, d);
     Post gp;
@@ -937,7 +969,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
              so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
-      const long before = gemm_launch_count() + dec_gemm_launch_count() + other_launch_count();
+      const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count();
       cudaGraph_t g = nullptr, cap = nullptr;
       if (loop_graph) {
         WL_CUDA(cudaGraphCreate(&g, 0));
@@ -970,7 +1002,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
         }
         WL_CUDA(cudaStreamEndCapture(st, &g));
       }
-      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + other_launch_count() - before;
+      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count() - before;
       c->capture_counted += ge.kernels;
       WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
       cudaGraphDestroy(g);
@@ -1286,6 +1318,50 @@ extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_
     throw;
   }
   cudaFree(da); cudaFree(db); cudaFree(dc); if (dbias) cudaFree(dbias);
+  API_END(c)
+}
+
+// mode 0/1/2/3 of wgemm (see gemm.cuh); out holds [R][n_out] floats (mode 1: the residual on input, the sum on output;
+// mode 2: gelu as fp32; mode 3: the K ranges summed on the host side of this hook)
+extern "C" int wl_test_wgemm(wl_ctx* c, const uint16_t* w_f16, const uint16_t* x_f16, const float* bias, float* out, int32_t R,
+                             int32_t n_out, int32_t K, int32_t mode) {
+  API_BEGIN(c)
+  WL_CHECK(w_f16 && x_f16 && out && mode >= 0 && mode <= 3, WL_ERR_ARG, "wl_test_wgemm: bad arguments");
+  WL_CHECK(wgemm_supported(R, K), WL_ERR_ARG, "wl_test_wgemm: unsupported shape R=%d K=%d", R, K);
+  __half *dw = nullptr, *dx = nullptr, *dh = nullptr;
+  float *db = nullptr, *dout = nullptr;
+  const size_t nw = (size_t)n_out * K, nx = (size_t)R * K, no = (size_t)R * n_out;
+  const int ks = wgemm_ksplit(K);
+  WL_CUDA(cudaMalloc((void**)&dw, nw * 2));
+  WL_CUDA(cudaMalloc((void**)&dx, nx * 2));
+  WL_CUDA(cudaMalloc((void**)&dh, no * 2));
+  WL_CUDA(cudaMalloc((void**)&dout, no * 4 * (size_t)std::max(1, ks)));
+  WL_CUDA(cudaMalloc((void**)&db, (size_t)n_out * 4));
+  try {
+    WL_CUDA(cudaMemcpy(dw, w_f16, nw * 2, cudaMemcpyHostToDevice));
+    WL_CUDA(cudaMemcpy(dx, x_f16, nx * 2, cudaMemcpyHostToDevice));
+    WL_CUDA(cudaMemset(dout, 0, no * 4 * (size_t)std::max(1, ks)));
+    if (mode == 1) WL_CUDA(cudaMemcpy(dout, out, no * 4, cudaMemcpyHostToDevice));
+    if (bias) WL_CUDA(cudaMemcpy(db, bias, (size_t)n_out * 4, cudaMemcpyHostToDevice));
+    WL_CUDA(cudaDeviceSynchronize());
+    wgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh, (long)no);
+    WL_CUDA(cudaStreamSynchronize(c->st));
+    if (mode == 2) {
+      std::vector<__half> h(no);
+      WL_CUDA(cudaMemcpy(h.data(), dh, no * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < no; ++i) out[i] = __half2float(h[i]);
+    } else if (mode == 3) {
+      std::vector<float> h(no * ks);
+      WL_CUDA(cudaMemcpy(h.data(), dout, h.size() * 4, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < no; ++i) { float a = 0.f; for (int q = 0; q < ks; ++q) a += h[(size_t)q * no + i]; out[i] = a; }
+    } else {
+      WL_CUDA(cudaMemcpy(out, dout, no * 4, cudaMemcpyDeviceToHost));
+    }
+  } catch (...) {
+    cudaFree(dw); cudaFree(dx); cudaFree(dh); cudaFree(dout); cudaFree(db);
+    throw;
+  }
+  cudaFree(dw); cudaFree(dx); cudaFree(dh); cudaFree(dout); cudaFree(db);
   API_END(c)
 }
 

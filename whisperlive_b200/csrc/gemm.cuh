@@ -78,6 +78,17 @@ long dec_gemm_launch_count();
 void dec_gemm_prime();
 void dec_gemm_tl_bind(unsigned long long* p);
 
+// Small-batch decode GEMM with fused epilogue (wgemm.cu, R <= 32 rows, mma.sync + bulk-copied weight slices).
+// mode 0: out_f32 = acc + bias; 1: out_f32 += acc + bias (in place); 2: out_f16 = gelu(acc + bias);
+// 3: out_f32[ks] = raw partial sum of K range ks (only when K > 1280)
+void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, int R, const float* bias, int mode, float* out_f32,
+           __half* out_f16, long part_stride);
+bool wgemm_supported(int R, int K);
+int wgemm_ksplit(int K);
+long wgemm_launch_count();
+void wgemm_prime();
+void wgemm_tl_bind(unsigned long long* p);
+
 // Tensor map over an operand view (dims sorted by stride) + the coordinate slots of (row, i1, i2).
 struct TmapInfo {
   CUtensorMap tm;

@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
   extern __shared__ uint8_t wg_smem_raw[];
   uint8_t* base = wg_smem_raw + ((128u - (smem_u32(wg_smem_raw) & 127u)) & 127u);
   const int pitch = p.kr * 2 + 64;                        // bytes per weight row: = 64 mod 128 -> conflict-free 16-byte reads
+  const int ntl = p.nf >> 3;                              // n-tiles (8 features) per CTA
   uint8_t* sW = base;                                     // [nf][pitch]
-  float* red = reinterpret_cast<float*>(sW + WG_MAX_NF * (WG_WARPS * WG_CH * 32 * 2 + 64));   // [8 warps][nf/8][MT][16*8]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + WG_WARPS * (WG_MAX_NF / 8) * MT * 128);
+  float* red = reinterpret_cast<float*>(sW + p.nf * pitch);   // [8 warps][ntl][MT][16*8]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + WG_WARPS * ntl * MT * 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
@@ -77,6 +78,17 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
 #pragma unroll 1
     for (int f = 0; f < nf; ++f) bulk_load_1d(sW + f * pitch, p.W + (long)(f0 + f) * p.K + k0, (uint32_t)(kr * 2), bar);
   }
+  // epilogue assignment: thread owns elements e = tid + i * 256 of the CTA's [MT*16 rows][nf features] tile.  Their bias
+  // (a weight) is fetched before the dependency wait and the residual right after it, so that the epilogue itself is
+  // shared-memory sums and one store -- no global round trip left at the end of the chain.
+  constexpr int EPI = (MT * 16 * WG_MAX_NF + WG_WARPS * 32 - 1) / (WG_WARPS * 32);
+  const int total = MT * 16 * nf;
+  float ebias[EPI], eres[EPI];
+#pragma unroll
+  for (int i = 0; i < EPI; ++i) {
+    const int e = tid + i * WG_WARPS * 32;
+    ebias[i] = (e < total && p.mode != 3 && p.bias != nullptr) ? __ldg(p.bias + f0 + e % nf) : 0.f;
+  }
   tl_stamp(TL_GEMM_PART, 0);
   pdl_wait();
   tl_stamp(TL_GEMM_PART, 1);
@@ -93,6 +105,12 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
       xa[mt][i][0] = (c < nchunks && r0 < p.R) ? __ldcg(reinterpret_cast<const uint4*>(xp + (long)r0 * p.K)) : z;
       xa[mt][i][1] = (c < nchunks && r1 < p.R) ? __ldcg(reinterpret_cast<const uint4*>(xp + (long)r1 * p.K)) : z;
     }
+#pragma unroll
+  for (int i = 0; i < EPI; ++i) {
+    const int e = tid + i * WG_WARPS * 32;
+    const int r = e / nf;
+    eres[i] = (p.mode == 1 && e < total && r < p.R) ? __ldcg(p.out_f32 + (long)r * p.n_out + f0 + (e - r * nf)) : 0.f;
+  }
   mbar_wait(bar, 0);
   const int ntiles = nf >> 3;
 #pragma unroll 1
@@ -116,35 +134,34 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
     // acc[mt] = D[row g | g+8][feature 2tq, 2tq+1] of this warp's K slice -> red[warp][nt][mt][row][feature]
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      float* rp = red + ((warp * (WG_MAX_NF / 8) + nt) * MT + mt) * 128;
+      float* rp = red + ((warp * ntl + nt) * MT + mt) * 128;
       *reinterpret_cast<float2*>(rp + g * 8 + 2 * tq) = make_float2(acc[mt][0], acc[mt][1]);
       *reinterpret_cast<float2*>(rp + (g + 8) * 8 + 2 * tq) = make_float2(acc[mt][2], acc[mt][3]);
     }
   }
   __syncthreads();
-  // fixed-order sum over the 8 warps + epilogue: element e = (mt, row, feature)
-  const int total = MT * 16 * nf;
-#pragma unroll 1
-  for (int e = tid; e < total; e += WG_WARPS * 32) {
-    const int f = e % nf, rr = e / nf;                    // rr = mt * 16 + row
-    const int r = rr, nt = f >> 3, fi = f & 7;
-    if (r >= p.R) continue;
-    const float* rp = red + ((nt * MT + (rr >> 4)) * 128) + (rr & 15) * 8 + fi;
-    float v = 0.f;
+  // fixed-order sum over the 8 warps + epilogue: element e = (mt * 16 + row, feature)
 #pragma unroll
-    for (int w = 0; w < WG_WARPS; ++w) v += rp[w * (WG_MAX_NF / 8) * MT * 128];
-    const int col = f0 + f;
-    if (p.mode != 3 && p.bias != nullptr) v += __ldg(p.bias + col);
-    const long o = (long)r * p.n_out + col;
-    if (p.mode == 0) p.out_f32[o] = v;
-    else if (p.mode == 1) p.out_f32[o] += v;
-    else if (p.mode == 2) p.out_f16[o] = __float2half_rn(gelu_erf(v));
-    else p.out_f32[(long)ks * p.part_stride + o] = v;
+  for (int i = 0; i < EPI; ++i) {
+    const int e = tid + i * WG_WARPS * 32;
+    const int r = e / nf, f = e - r * nf;
+    if (e < total && r < p.R) {
+      const float* rp = red + (((f >> 3) * MT + (r >> 4)) * 128) + (r & 15) * 8 + (f & 7);
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < WG_WARPS; ++w) v += rp[w * ntl * MT * 128];
+      v += ebias[i];
+      const long o = (long)r * p.n_out + f0 + f;
+      if (p.mode == 0) p.out_f32[o] = v;
+      else if (p.mode == 1) p.out_f32[o] = eres[i] + v;
+      else if (p.mode == 2) p.out_f16[o] = __float2half_rn(gelu_erf(v));
+      else p.out_f32[(long)ks * p.part_stride + o] = v;
+    }
   }
 }
 
-static int wg_smem_bytes(int MT) {
-  return 128 + WG_MAX_NF * (WG_WARPS * WG_CH * 32 * 2 + 64) + WG_WARPS * (WG_MAX_NF / 8) * MT * 128 * 4 + 64;
+static int wg_smem_bytes(int MT, int nf = WG_MAX_NF, int kr = WG_WARPS * WG_CH * 32) {
+  return 128 + nf * (kr * 2 + 64) + WG_WARPS * (nf / 8) * MT * 128 * 4 + 64;
 }
 void wgemm_tl_bind(unsigned long long* p) { tl_bind_tu(p); }
 void wgemm_prime() {
@@ -181,8 +198,8 @@ void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, 
   while (nf < WG_MAX_NF && cdiv(n_out, nf) * ksplit > sms) nf += 8;
   p.nf = nf;
   const int grid = cdiv(n_out, nf) * ksplit;
-  if (R <= 16) launch_kernel(wgemm_kernel<1>, dim3(grid), dim3(WG_WARPS * 32), (size_t)wg_smem_bytes(1), st, p);
-  else launch_kernel(wgemm_kernel<2>, dim3(grid), dim3(WG_WARPS * 32), (size_t)wg_smem_bytes(2), st, p);
+  if (R <= 16) launch_kernel(wgemm_kernel<1>, dim3(grid), dim3(WG_WARPS * 32), (size_t)wg_smem_bytes(1, nf, p.kr), st, p);
+  else launch_kernel(wgemm_kernel<2>, dim3(grid), dim3(WG_WARPS * 32), (size_t)wg_smem_bytes(2, nf, p.kr), st, p);
   g_wgemm_launches++;
 }
 

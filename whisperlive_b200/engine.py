@@ -398,6 +398,24 @@ class B200Whisper:
             _lib.check(self.lib, self.ctx, rc, "wl_decode_logits")
         return [out[off[b]:off[b + 1]] for b in range(B)]
 
+    def test_wgemm(self, w: np.ndarray, x: np.ndarray, bias: Optional[np.ndarray] = None, mode: int = 0,
+                   resid: Optional[np.ndarray] = None) -> np.ndarray:
+        """Y[R, n_out] = X[R, K] W[n_out, K]^T through the small-batch decode GEMM (wl_test_wgemm)."""
+        w16 = np.ascontiguousarray(w, dtype=np.float16)
+        x16 = np.ascontiguousarray(x, dtype=np.float16)
+        n_out, K = w16.shape
+        R = x16.shape[0]
+        out = np.zeros((R, n_out), dtype=np.float32) if resid is None else np.ascontiguousarray(resid, dtype=np.float32).copy()
+        bp = None
+        if bias is not None:
+            bias = np.ascontiguousarray(bias, dtype=np.float32)
+            bp = _lib.ptr(bias, C.c_float)
+        with self._lock:
+            rc = self.lib.wl_test_wgemm(self.ctx, _lib.ptr(w16.view(np.uint16), C.c_uint16), _lib.ptr(x16.view(np.uint16), C.c_uint16),
+                                        bp, _lib.ptr(out, C.c_float), R, n_out, K, int(mode))
+            _lib.check(self.lib, self.ctx, rc, "wl_test_wgemm")
+        return out
+
     def test_gemm(self, a: np.ndarray, b: np.ndarray, bias: Optional[np.ndarray] = None, transposed_store: bool = False,
                   gelu: bool = False, use_simt: bool = False) -> np.ndarray:
         """C[z] = A[z] @ B[z]^T through the tcgen05 kernel (or the CUDA-core checker)."""
