@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WL_ABI_VERSION 1
+#define WL_ABI_VERSION 2
 
 typedef struct wl_ctx wl_ctx;
 
@@ -64,6 +64,8 @@ typedef struct wl_gen_opts {
   int32_t n_suppress;
   int32_t use_cuda_graph;            /* 1: capture the decoder step once per call shape */
   const int32_t* max_length_per_stream; /* optional [B]: overrides max_length per stream (ragged max_new_tokens) */
+  int32_t prefill;                   /* K8: 0 = library default (batched prefill of the prompt), 1 = on, 2 = off (one decode
+                                        step per prompt token; the parity tests compare the two) */
 } wl_gen_opts;
 
 int wl_init(const wl_config* cfg, wl_ctx** out);
@@ -129,6 +131,14 @@ float wl_last_device_ms(wl_ctx* ctx, int32_t which /*0 mel, 1 encode, 2 generate
 /* enable = 1: wl_generate calls made WITHOUT a CUDA graph bracket every cross-attention launch (K11, the dominant
  * decode kernel) with CUDA events on the library stream -- bench.py's live roofline measurement.  Resets the sums. */
 int wl_profile_cross_attn(wl_ctx* ctx, int32_t enable);
+/* K1 with the features kept in HBM (replaces FeatureExtractor + pad_or_trim + the feature upload of encode inside
+ * B200WhisperModel.transcribe_batch; reference call sites transcriber_faster_whisper.py:862, :1115-1127, :1348):
+ * wl_mel_device computes the log-mel of B waveforms (frames_out[b] = len/160 + 1, like wl_mel) and keeps it resident
+ * until the next wl_mel_device call; wl_encode_windows encodes B windows cut from it -- window w is frames
+ * [seek, seek + len) of stream win_stream[w], zero-padded to 3000 on the device -- into fresh encoder slots. */
+int wl_mel_device(wl_ctx* ctx, const float* pcm, const int64_t* offsets, int32_t B, int32_t* frames_out);
+int wl_encode_windows(wl_ctx* ctx, int32_t B, const int32_t* win_stream, const int32_t* win_seek, const int32_t* win_len,
+                      int32_t* slots_out);
 /* resident-input variants for bench.py `value`: inputs already uploaded by the previous call of the
  * host variant are reused (no H2D, no D2H) */
 int wl_mel_resident(wl_ctx* ctx);

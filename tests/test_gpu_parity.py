@@ -335,6 +335,34 @@ def test_generate_with_prefix_matches_oracle(beam):
     # stream 0: the history already holds <|0.00|> + text, so the first generated token is free to be text
 
 
+@pytest.mark.parametrize("name,beam", [("micro.en", 5), ("tiny", 1), ("micro", 4)])
+def test_batched_prefill_equals_token_by_token(name, beam):
+    """K8: prompts of 1 .. 230 tokens (sot_prev + previous text + sot sequence, transcriber_faster_whisper.py:1480-1513)
+    prefilled in one batched pass give the hypotheses, scores and no-speech probabilities of feeding the prompt one
+    decode step per token -- and the oracle's, which prefills like CT2 does."""
+    eng, orc = engine(name, seed=0)
+    dims, sp = eng.dims, orc.spec
+    feats = np.stack([feats_for(dims, 6.0, 1), feats_for(dims, 9.0, 2), feats_for(dims, 5.0, 3), feats_for(dims, 12.0, 4)])
+    enc, oenc = eng.encode(feats), orc.encode(feats)
+    base = [sp.sot] if not dims.multilingual else [sp.sot, sp.sot + 1, sp.sot + 1 + dims.num_languages + 1]
+    rng = np.random.default_rng(17)
+    prev = lambda n: [sp.timestamp_begin - 3] + rng.integers(256, 40000, n).tolist()     # <|startofprev|> + text
+    prompts = [base, prev(222) + base, prev(37) + base, prev(8) + base + [sp.no_timestamps]]
+    kw = dict(beam_size=beam, suppress_tokens=[1, 2, 3], max_length=448)
+    a = eng.generate(enc, prompts, prefill=True, **kw)
+    b = eng.generate(enc, prompts, prefill=False, **kw)
+    for x, y, p in zip(a, b, prompts):
+        assert x.steps < y.steps or len(p) == 1, "the prefilled prompt must not cost decode steps"
+        assert abs(x.no_speech_prob - y.no_speech_prob) < 5e-3
+        if x.sequences_ids[0] != y.sequences_ids[0]:      # the GEMM kernels differ (tcgen05 tiles vs decode path): near-ties may flip
+            print("prefill vs stepwise differ:", x.scores, y.scores)
+            assert abs(x.scores[0] - y.scores[0]) < SCORE_TOL
+        else:
+            assert abs(x.scores[0] - y.scores[0]) < 5e-3
+    ref = orc.generate(oenc, prompts, **kw)
+    _compare_generation(a, ref, f"prefill {name} beam{beam}", orc, oenc, prompts, kw, eng=eng, enc=enc)
+
+
 class _EngineStep:
     """oracle.search step function backed by the ENGINE's logits (teacher-forced wl_decode_logits over the
     full prefix of every live row): lets the oracle's search run on exactly the numbers the engine sees."""

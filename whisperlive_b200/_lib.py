@@ -10,7 +10,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwlb200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -36,7 +36,7 @@ class WlGenOpts(C.Structure):
         ("max_length", C.c_int32), ("suppress_blank", C.c_int32), ("max_initial_timestamp_index", C.c_int32),
         ("sampling_topk", C.c_int32), ("sampling_temperature", C.c_float), ("seed", C.c_uint32),
         ("suppress_tokens", c_i32p), ("n_suppress", C.c_int32), ("use_cuda_graph", C.c_int32),
-        ("max_length_per_stream", c_i32p),
+        ("max_length_per_stream", c_i32p), ("prefill", C.c_int32),
     ]
 
 
@@ -65,6 +65,8 @@ SIGNATURES = {
     "wl_kernel_launches": (C.c_int64, [C.c_void_p]),
     "wl_last_device_ms": (C.c_float, [C.c_void_p, C.c_int32]),
     "wl_profile_cross_attn": (C.c_int, [C.c_void_p, C.c_int32]),
+    "wl_mel_device": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int32, c_i32p]),
+    "wl_encode_windows": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p]),
     "wl_mel_resident": (C.c_int, [C.c_void_p]),
     "wl_encode_resident": (C.c_int, [C.c_void_p, C.c_int32, c_i32p]),
 }

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   *reinterpret_cast<float2*>(q + 2 * lane) = qv;
   *reinterpret_cast<float2*>(vnew + 2 * lane) = vv;
   {
-    const long o = (long)r * row_stride + ((long)h * T_MAX + pos) * 64 + 2 * lane;
+    const int wr = s.wrow != nullptr ? s.wrow[r] : r;
+    const long o = (long)wr * row_stride + ((long)h * T_MAX + pos) * 64 + 2 * lane;
     *reinterpret_cast<__half2*>(kc + o) = __floats2half2_rn(kv.x, kv.y);
     *reinterpret_cast<__half2*>(vc + o) = __floats2half2_rn(vv.x, vv.y);
   }

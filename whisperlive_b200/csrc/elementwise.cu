@@ -23,6 +23,25 @@ void cast_weight_f16(cudaStream_t st, const float* in, __half* out, long a, long
   WL_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------- gather_windows
+__global__ void gather_windows_kernel(const float* __restrict__ mel, const long* __restrict__ mel_off, const int* __restrict__ frames,
+                                      const int* __restrict__ win_stream, const int* __restrict__ win_seek,
+                                      const int* __restrict__ win_len, float* __restrict__ feat, int n_mels) {
+  const int w = blockIdx.z, m = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3000) return;
+  const int sidx = win_stream[w], T = frames[sidx], seek = win_seek[w], len = win_len[w];
+  float v = 0.f;
+  if (t < len && seek + t < T) v = mel[mel_off[sidx] + (long)m * T + seek + t];
+  feat[((long)w * n_mels + m) * 3000 + t] = v;
+}
+void gather_windows(cudaStream_t st, const float* mel, const long* mel_off, const int* frames, const int* win_stream, const int* win_seek,
+                    const int* win_len, float* feat, int n_windows, int n_mels) {
+  dim3 grid(cdiv(3000, 256), n_mels, n_windows);
+  gather_windows_kernel<<<grid, 256, 0, st>>>(mel, mel_off, frames, win_stream, win_seek, win_len, feat, n_mels);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
 // ---------------------------------------------------------------------------- prep_features
 // [B][n_mels][3000] f32 -> [B][3002][n_mels] fp16 with one zero row before and after (conv k=3, pad=1
 // becomes a plain strided GEMM over overlapping rows).  32x32 smem transpose tiles.

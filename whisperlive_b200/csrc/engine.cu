@@ -110,6 +110,21 @@ struct wl_ctx {
   // WLB200_TIMELINE: in-graph per-kernel timestamps (common.cuh), dumped after every wl_generate
   unsigned long long* tl_dev = nullptr;
   std::string tl_path;
+  // resident log-mel of the last wl_mel_device call (features never leave the GPU between mel and encoder)
+  float *res_pcm = nullptr, *res_mel = nullptr;
+  long res_pcm_cap = 0, res_mel_cap = 0;
+  long *res_off = nullptr, *res_ooff = nullptr;
+  int *res_frames = nullptr, *win_meta = nullptr;
+  std::vector<int> res_frames_h;
+  // K8 batched prefill workspaces (allocated on first use, grown on demand)
+  struct Prefill {
+    long cap_rows = 0;
+    int *tok = nullptr, *pos = nullptr, *active = nullptr, *wrow = nullptr, *vslot = nullptr, *vdone = nullptr, *sel = nullptr;
+    short* src = nullptr;
+    float *x = nullptr, *qkv = nullptr, *qc = nullptr, *xpart = nullptr;
+    __half *xn = nullptr, *att = nullptr, *h = nullptr;
+    long rows_done = 0, calls = 0;   // statistics
+  } pf;
   float* stage_f32 = nullptr;   // wl_load_tensor staging (freed by wl_finalize_weights)
   size_t stage_cap = 0;
 };
@@ -346,6 +361,10 @@ static void build_mel_tables(wl_ctx* c) {
   c->mel_range = dalloc<int>(c, rg.size());
   WL_CUDA(cudaMemcpy(c->mel_range, rg.data(), rg.size() * 4, cudaMemcpyHostToDevice));
   c->mel_gmax = dalloc<unsigned>(c, c->Bm);
+  c->res_off = dalloc<long>(c, c->Bm + 1);
+  c->res_ooff = dalloc<long>(c, c->Bm + 1);
+  c->res_frames = dalloc<int>(c, c->Bm);
+  c->win_meta = dalloc<int>(c, 3 * (size_t)c->Bm);
   c->mel_off = dalloc<long>(c, c->Bm + 1);
   c->mel_ooff = dalloc<long>(c, c->Bm + 1);
 }
@@ -521,6 +540,83 @@ extern "C" int wl_mel(wl_ctx* c, const float* pcm, const int64_t* offsets, int32
   WL_CUDA(cudaMemcpyAsync(out + out_offsets[0], c->mel_out, ooff[B] * sizeof(float), cudaMemcpyDeviceToHost, c->st));
   WL_CUDA(cudaStreamSynchronize(c->st));
   WL_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1));
+  API_END(c)
+}
+
+// K1 with the result kept on the device: PCM up, log-mel stays in HBM until the next wl_mel_device call; the windows the
+// encoder consumes are gathered from it on the device (wl_encode_windows).  Round 1 copied the features to the host,
+// zero-padded them there and copied them back (110 MB of PCIe traffic and ~28 ms per 32-stream step).
+extern "C" int wl_mel_device(wl_ctx* c, const float* pcm, const int64_t* offsets, int32_t B, int32_t* frames_out) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized, WL_ERR_STATE, "weights not finalized");
+  WL_CHECK(pcm && offsets && frames_out && B >= 1 && B <= c->Bm, WL_ERR_ARG, "wl_mel_device: bad arguments (B=%d, max %d)", B, c->Bm);
+  const long total = offsets[B] - offsets[0];
+  int max_frames = 0;
+  std::vector<long> off(B + 1), ooff(B + 1, 0);
+  c->res_frames_h.assign(B, 0);
+  for (int b = 0; b <= B; ++b) off[b] = offsets[b] - offsets[0];
+  for (int b = 0; b < B; ++b) {
+    const long n = off[b + 1] - off[b];
+    WL_CHECK(n > 0, WL_ERR_ARG, "wl_mel_device: empty waveform for stream %d", b);
+    const int T = (int)(n / 160) + 1;
+    max_frames = std::max(max_frames, T);
+    c->res_frames_h[b] = T;
+    frames_out[b] = T;
+    ooff[b + 1] = ooff[b] + (long)T * c->n_mels;
+  }
+  if (total > c->res_pcm_cap) {
+    c->res_pcm = dalloc<float>(c, total + total / 4, false);
+    c->res_pcm_cap = total + total / 4;
+  }
+  if (ooff[B] > c->res_mel_cap) {
+    c->res_mel = dalloc<float>(c, ooff[B] + ooff[B] / 4, false);
+    c->res_mel_cap = ooff[B] + ooff[B] / 4;
+  }
+  cudaStream_t st = c->st;
+  WL_CUDA(cudaMemcpyAsync(c->res_pcm, pcm + offsets[0], total * sizeof(float), cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(c->res_off, off.data(), (B + 1) * sizeof(long), cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(c->res_ooff, ooff.data(), (B + 1) * sizeof(long), cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(c->res_frames, c->res_frames_h.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  MelTables t{c->mel_window, c->mel_twiddle, c->mel_filt, c->mel_range, c->n_mels};
+  WL_CUDA(cudaEventRecord(c->ev0, st));
+  mel_forward(st, c->res_pcm, c->res_off, c->res_mel, c->res_ooff, c->mel_gmax, t, B, max_frames);
+  WL_CUDA(cudaEventRecord(c->ev1, st));
+  WL_CUDA(cudaStreamSynchronize(st));   // the caller's PCM and the staging vectors above may go away
+  WL_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1));
+  API_END(c)
+}
+
+static void encode_impl(wl_ctx* c, const float* features_host, int B, const int* slots, bool resident);
+
+extern "C" int wl_encode_windows(wl_ctx* c, int32_t B, const int32_t* win_stream, const int32_t* win_seek, const int32_t* win_len,
+                                 int32_t* slots_out) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized && win_stream && win_seek && win_len && slots_out && B >= 1 && B <= c->Bm, WL_ERR_ARG,
+           "wl_encode_windows: bad arguments (B=%d, max %d)", B, c->Bm);
+  const int ns = (int)c->res_frames_h.size();
+  for (int b = 0; b < B; ++b) {
+    WL_CHECK(win_stream[b] >= 0 && win_stream[b] < ns, WL_ERR_ARG, "wl_encode_windows: window %d names stream %d (wl_mel_device holds %d)", b, win_stream[b], ns);
+    WL_CHECK(win_seek[b] >= 0 && win_len[b] >= 0 && win_len[b] <= 3000 && win_seek[b] + win_len[b] <= c->res_frames_h[win_stream[b]],
+             WL_ERR_ARG, "wl_encode_windows: window %d [%d, +%d) is outside the %d resident frames", b, win_seek[b], win_len[b],
+             c->res_frames_h[win_stream[b]]);
+  }
+  WL_CHECK((int)c->slot_free.size() >= B, WL_ERR_NOMEM, "wl_encode_windows: %d encoder slots requested, %d free", B, (int)c->slot_free.size());
+  for (int b = 0; b < B; ++b) {
+    slots_out[b] = c->slot_free.back();
+    c->slot_free.pop_back();
+    c->slot_used[slots_out[b]] = 1;
+  }
+  try {
+    std::vector<int> meta(3 * (size_t)B);
+    for (int b = 0; b < B; ++b) { meta[b] = win_stream[b]; meta[B + b] = win_seek[b]; meta[2 * B + b] = win_len[b]; }
+    WL_CUDA(cudaMemcpyAsync(c->win_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    gather_windows(c->st, c->res_mel, c->res_ooff, c->res_frames, c->win_meta, c->win_meta + B, c->win_meta + 2 * B, c->feat32, B, c->n_mels);
+    WL_CUDA(cudaStreamSynchronize(c->st));   // meta goes out of scope
+    encode_impl(c, nullptr, B, slots_out, true);
+  } catch (...) {
+    for (int b = 0; b < B; ++b) { c->slot_used[slots_out[b]] = 0; c->slot_free.push_back(slots_out[b]); }
+    throw;
+  }
   API_END(c)
 }
 
@@ -782,27 +878,32 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   // whose epilogue writes FINAL values (bias, residual, GELU fused), so LayerNorm / attention read one value instead of
   // summing partials and the GELU-cast launch is gone: 12 launches per layer instead of 13, each a fraction of the code.
   static const bool wg_env = [] { const char* e = getenv("WLB200_WGEMM"); return e ? atoi(e) != 0 : true; }();
-  const bool small = wg_env && !simt_env && !fuse && wgemm_supported(R, d) && wgemm_supported(R, ff);
+  // (one m16 tile only: with two, every CTA re-reads 82 KB of X from L2 and the launch costs 8 us -- measured; rows
+  // 17..32 take the tcgen05 path below until the K split moves into a cluster)
+  static const int wg_max_rows = [] { const char* e = getenv("WLB200_WGEMM_ROWS"); return e ? atoi(e) : 16; }();
+  const bool small = wg_env && !simt_env && !fuse && R <= wg_max_rows && wgemm_supported(R, d) && wgemm_supported(R, ff);
   auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
   for (int l = 0; small && l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
+    const long dd2 = (long)d * d * 2;   // bytes of a d x d fp16 matrix; every launch prefetches the NEXT layer's weights into L2
+    const __half* next_qkv = l + 1 < c->Ld ? c->dec[l + 1].w_qkv : nullptr;
     layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
-    wgemm(st, L.w_qkv, 3 * d, d, c->dxn, R, L.b_qkv, 0, c->part1, nullptr, 0);
+    wgemm(st, L.w_qkv, 3 * d, d, c->dxn, R, L.b_qkv, 0, c->part1, nullptr, 0, L.w_o, dd2);
     decoder_self_attn(st, s, plain(c->part1), c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
-    wgemm(st, L.w_o, d, d, c->datt, R, L.b_o, 1, c->dx, nullptr, 0);
+    wgemm(st, L.w_o, d, d, c->datt, R, L.b_o, 1, c->dx, nullptr, 0, L.w_qc, dd2);
     layernorm_update_rows(st, c->dx, PartialSrc(), L.ln2_g, L.ln2_b, c->dxn, R, d);
-    wgemm(st, L.w_qc, d, d, c->dxn, R, L.b_qc, 0, c->part1, nullptr, 0);
+    wgemm(st, L.w_qc, d, d, c->dxn, R, L.b_qc, 0, c->part1, nullptr, 0, L.w_oc, dd2);
     cross(l, plain(c->part1));
-    wgemm(st, L.w_oc, d, d, c->datt, R, L.b_oc, 1, c->dx, nullptr, 0);
+    wgemm(st, L.w_oc, d, d, c->datt, R, L.b_oc, 1, c->dx, nullptr, 0, L.w_fc1, 4 * dd2);
     layernorm_update_rows(st, c->dx, PartialSrc(), L.ln3_g, L.ln3_b, c->dxn, R, d);
-    wgemm(st, L.w_fc1, ff, d, c->dxn, R, L.b_fc1, 2, nullptr, c->dh, 0);
+    wgemm(st, L.w_fc1, ff, d, c->dxn, R, L.b_fc1, 2, nullptr, c->dh, 0, L.w_fc2, 4 * dd2);
     const int ks2 = wgemm_ksplit(ff);
     if (ks2 == 1) {
-      wgemm(st, L.w_fc2, d, ff, c->dh, R, L.b_fc2, 1, c->dx, nullptr, 0);
+      wgemm(st, L.w_fc2, d, ff, c->dh, R, L.b_fc2, 1, c->dx, nullptr, 0, next_qkv, 3 * dd2);
       pending = PartialSrc();
     } else {   // K = 4d is split over CTAs: the next LayerNorm folds the ranges (+ bias) into x
-      wgemm(st, L.w_fc2, d, ff, c->dh, R, nullptr, 3, c->part2, nullptr, (long)c->Rm * d);
+      wgemm(st, L.w_fc2, d, ff, c->dh, R, nullptr, 3, c->part2, nullptr, (long)c->Rm * d, next_qkv, 3 * dd2);
       pending.ptr = c->part2; pending.nsplit = ks2; pending.stride = (long)c->Rm * d; pending.bias = L.b_fc2;
     }
   }
@@ -844,6 +945,131 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   search_streams(st, s, so, vi, B);
 }
 
+// ------------------------------------------------------------------------------------------ K8 batched prefill
+constexpr int PF_VCHUNK = 128;   // cross-attention groups (8 rows each) per launch
+
+static void prefill_reserve(wl_ctx* c, long rows) {
+  wl_ctx::Prefill& f = c->pf;
+  if (rows <= f.cap_rows) return;
+  const long cap = (rows + 1023) / 1024 * 1024;
+  const int d = c->d, ff = 4 * c->d;
+  // (earlier, smaller buffers stay in c->allocs until wl_destroy: growth happens a handful of times per process)
+  f.tok = dalloc<int>(c, cap); f.pos = dalloc<int>(c, cap); f.active = dalloc<int>(c, cap); f.wrow = dalloc<int>(c, cap);
+  f.vslot = dalloc<int>(c, cap / 8 + PF_VCHUNK); f.vdone = dalloc<int>(c, cap / 8 + PF_VCHUNK);
+  if (!f.sel) f.sel = dalloc<int>(c, 3 * (size_t)c->Rm + 16);
+  f.src = dalloc<short>(c, cap * T_MAX, false);
+  f.x = dalloc<float>(c, cap * d, false); f.qkv = dalloc<float>(c, cap * 3 * d, false); f.qc = dalloc<float>(c, cap * d, false);
+  f.xn = dalloc<__half>(c, cap * d, false); f.att = dalloc<__half>(c, cap * d, false); f.h = dalloc<__half>(c, cap * ff, false);
+  if (!f.xpart) f.xpart = dalloc<float>(c, (size_t)PF_VCHUNK * c->H * 12 * MAX_ROWS_PER_STREAM * 66, false);
+  f.cap_rows = cap;
+}
+
+// All prompt positions but the last of every stream through the decoder stack in one pass.  hp = prompts [B][T_MAX]
+// (pinned host), P / sot / slots per stream.  Leaves the self-attention cache filled for positions 0 .. P-2 in the
+// stream's first decode row (b * Kr) and the no-speech probability of streams whose sot lies inside the prompt.
+static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* P, const int* sot, const int32_t* slots) {
+  const int d = c->d, H = c->H, ff = 4 * c->d;
+  cudaStream_t st = c->st;
+  WL_CUDA(cudaMemsetAsync(c->ds.no_speech, 0, B * sizeof(float), st));
+  std::vector<int> tok, pos, act, wrow, vslot, rowbase(B, 0);
+  for (int b = 0; b < B; ++b) {
+    rowbase[b] = (int)tok.size();
+    const int n = P[b] - 1, n8 = (n + 7) / 8 * 8;
+    for (int i = 0; i < n8; ++i) {
+      tok.push_back(i < n ? hp[(size_t)b * T_MAX + i] : 0);
+      pos.push_back(i < n ? i : 0);
+      act.push_back(i < n ? 1 : 0);
+      wrow.push_back(b * Kr);
+    }
+    for (int g = 0; g < n8 / 8; ++g) vslot.push_back(slots[b]);
+  }
+  const long M = (long)tok.size();
+  if (M == 0) return;
+  prefill_reserve(c, M);
+  wl_ctx::Prefill& f = c->pf;
+  const int NV = (int)vslot.size();
+  WL_CUDA(cudaMemcpyAsync(f.tok, tok.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.pos, pos.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.active, act.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.wrow, wrow.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.vslot, vslot.data(), NV * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemsetAsync(f.vdone, 0, NV * 4, st));
+  prefill_embed(st, f.tok, f.pos, f.active, f.wrow, c->emb, c->pos_dec, f.x, f.src, (int)M, d);
+  WL_CUDA(cudaStreamSynchronize(st));   // the host vectors above go out of scope below
+  DecodeState sv = c->ds;
+  sv.active = f.active; sv.pos = f.pos; sv.src = f.src; sv.wrow = f.wrow;
+  auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
+  const long slot_sz = (long)S_ENC * d;
+  for (int l = 0; l < c->Ld; ++l) {
+    const DecLayer& L = c->dec[l];
+    __half* kc = c->kcache + (long)l * c->cache_layer_stride;
+    __half* vc = c->vcache + (long)l * c->cache_layer_stride;
+    layernorm_rows(st, f.x, L.ln1_g, L.ln1_b, f.xn, nullptr, M, d);
+    {
+      GemmEpilogue e;
+      e.out = f.qkv; e.out_f32 = 1; e.ldm = 3 * d; e.bias = L.b_qkv;
+      gemm_tn(st, opnd(f.xn, M, d, d), opnd(L.w_qkv, 3 * d, d, d), (int)M, 3 * d, d, e);
+    }
+    prefill_kv_write(st, f.qkv, f.pos, f.active, f.wrow, kc, vc, c->cache_row_stride, (int)M, H, d);
+    decoder_self_attn(st, sv, plain(f.qkv), kc, vc, c->cache_row_stride, f.att, (int)M, H, d);
+    {
+      GemmEpilogue e;
+      e.out = f.x; e.out_f32 = 1; e.ldm = d; e.bias = L.b_o; e.resid = f.x; e.rldm = d;
+      gemm_tn(st, opnd(f.att, M, d, d), opnd(L.w_o, d, d, d), (int)M, d, d, e);
+    }
+    layernorm_rows(st, f.x, L.ln2_g, L.ln2_b, f.xn, nullptr, M, d);
+    {
+      GemmEpilogue e;
+      e.out = f.qc; e.out_f32 = 1; e.ldm = d; e.bias = L.b_qc;
+      gemm_tn(st, opnd(f.xn, M, d, d), opnd(L.w_qc, d, d, d), (int)M, d, d, e);
+    }
+    for (int v0 = 0; v0 < NV; v0 += PF_VCHUNK) {   // groups of 8 rows against their stream's encoder K/V
+      const int Bv = std::min(PF_VCHUNK, NV - v0);
+      DecodeState sx = c->ds;
+      sx.done = f.vdone + v0; sx.slot = f.vslot + v0;
+      CrossAttnWorkspace ws;
+      ws.part = f.xpart; ws.probs = nullptr;
+      const int nsp = cross_attn_pick_nsplit(Bv, H, c->num_sms, MAX_ROWS_PER_STREAM);
+      decoder_cross_attn(st, sx, plain(f.qc + (long)v0 * 8 * d), c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz,
+                         c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz, slot_sz, ws, f.att + (long)v0 * 8 * d, Bv, MAX_ROWS_PER_STREAM, H, d, nsp);
+    }
+    {
+      GemmEpilogue e;
+      e.out = f.x; e.out_f32 = 1; e.ldm = d; e.bias = L.b_oc; e.resid = f.x; e.rldm = d;
+      gemm_tn(st, opnd(f.att, M, d, d), opnd(L.w_oc, d, d, d), (int)M, d, d, e);
+    }
+    layernorm_rows(st, f.x, L.ln3_g, L.ln3_b, f.xn, nullptr, M, d);
+    {
+      GemmEpilogue e;
+      e.out = f.h; e.ldm = ff; e.bias = L.b_fc1; e.gelu = 1;
+      gemm_tn(st, opnd(f.xn, M, d, d), opnd(L.w_fc1, ff, d, d), (int)M, ff, d, e);
+    }
+    {
+      GemmEpilogue e;
+      e.out = f.x; e.out_f32 = 1; e.ldm = d; e.bias = L.b_fc2; e.resid = f.x; e.rldm = d;
+      gemm_tn(st, opnd(f.h, M, ff, ff), opnd(L.w_fc2, d, ff, ff), (int)M, d, ff, e);
+    }
+  }
+  // no-speech probability of the streams whose <|startoftranscript|> lies inside the prefilled part: final LayerNorm +
+  // vocabulary projection of that one row per stream (through the decode step's own kernels), softmax, pick
+  std::vector<int> sel, tgt, oidx;
+  for (int b = 0; b < B; ++b)
+    if (sot[b] >= 0 && sot[b] < P[b] - 1) { sel.push_back(rowbase[b] + sot[b]); tgt.push_back(c->cfg.no_speech); oidx.push_back(b); }
+  const int ns = (int)sel.size();
+  if (ns > 0) {
+    std::vector<int> up(3 * (size_t)ns);
+    for (int i = 0; i < ns; ++i) { up[i] = sel[i]; up[ns + i] = tgt[i]; up[2 * ns + i] = oidx[i]; }
+    WL_CUDA(cudaMemcpyAsync(f.sel, up.data(), up.size() * 4, cudaMemcpyHostToDevice, st));
+    gather_rows(st, f.x, f.sel, c->dx, ns, d);
+    layernorm_update_rows(st, c->dx, PartialSrc(), c->lnf_g, c->lnf_b, c->dxn, ns, d);
+    dec_gemm(st, c->emb, c->V, d, c->dxn, ns, c->logits, c->Vld, 0, 1);
+    row_prob(st, c->logits, c->V, c->Vld, f.sel + ns, f.sel + 2 * ns, c->ds.no_speech, ns);
+    WL_CUDA(cudaStreamSynchronize(st));
+  }
+  f.rows_done += M;
+  f.calls += 1;
+}
+
 static VocabIds vocab_ids(wl_ctx* c) {
   VocabIds v;
   v.vocab = c->V; v.vocab_ld = c->Vld; v.eot = c->cfg.eot; v.sot = c->cfg.sot; v.no_speech = c->cfg.no_speech;
@@ -853,11 +1079,11 @@ static VocabIds vocab_ids(wl_ctx* c) {
 
 // upload prompts & per-stream metadata; returns max steps
 static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t* prompts, const int32_t* off, int max_length,
-                          bool forced, const int32_t* max_len_ps = nullptr) {
+                          bool forced, const int32_t* max_len_ps = nullptr, int* max_new_out = nullptr) {
   ensure_host(c, (size_t)B * (T_MAX + 16), 16);
   int* hp = c->h_int;                      // [B][T_MAX]
   int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len, pre_n, pre_last, pre_penult, pre_lts
-  int max_steps = 0;
+  int max_steps = 0, max_new = 0;
   for (int b = 0; b < B; ++b) {
     const int P = off[b + 1] - off[b];
     WL_CHECK(P >= 1 && P <= T_MAX, WL_ERR_ARG, "stream %d: prompt length %d out of range", b, P);
@@ -876,6 +1102,7 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
       n_new = std::min(ml / 2, ml - P);
       WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, ml);
       max_steps = std::max(max_steps, P - 1 + n_new);
+      max_new = std::max(max_new, n_new);
     } else {
       max_steps = std::max(max_steps, P);
     }
@@ -914,6 +1141,7 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
   WL_CUDA(cudaMemcpyAsync(s.pre_last, meta + 7 * B, B * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaMemcpyAsync(s.pre_penult, meta + 8 * B, B * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaMemcpyAsync(s.pre_lts, meta + 9 * B, B * 4, cudaMemcpyHostToDevice, st));
+  if (max_new_out) *max_new_out = max_new;
   return max_steps;
 }
 
@@ -947,12 +1175,25 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     const int t = o->suppress_tokens[i];
     if (t >= 0 && t < c->V) mask[t >> 5] |= 1u << (t & 31);
   }
-  const int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false, o->max_length_per_stream);
+  int max_new = 0;
+  int max_steps = upload_streams(c, slots, B, prompts, prompt_off, o->max_length, false, o->max_length_per_stream, &max_new);
+  // K8: every prompt position but the last goes through the decoder in ONE batched pass (WLB200_PREFILL=0: one decode
+  // step per prompt token, the round-1 behaviour)
+  static const bool prefill_env = [] { const char* e = getenv("WLB200_PREFILL"); return e ? atoi(e) != 0 : true; }();
+  const bool prefilled = o->prefill == 1 || (o->prefill == 0 && prefill_env);
+  if (prefilled) max_steps = max_new;
   WL_CUDA(cudaMemcpyAsync(c->suppress_mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
   const unsigned seed_host = o->seed;
   WL_CUDA(cudaMemcpyAsync(c->ds.seed, &seed_host, sizeof(unsigned), cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaEventRecord(c->ev0, st));
-  decode_init(st, c->ds, so, vi, B, R);
+  if (prefilled) {
+    // upload_streams staged the prompts in pinned host memory: h_int = [B][T_MAX] tokens, then the per-stream metadata
+    WL_CUDA(cudaStreamSynchronize(st));
+    const int* hp = c->h_int;
+    const int* meta = c->h_int + (size_t)B * T_MAX;
+    prefill_forward(c, B, Kr, hp, meta + 1 * B, meta + 2 * B, slots);
+  }
+  decode_init(st, c->ds, so, vi, B, R, prefilled ? 1 : 0);
   const int nsplit = cross_attn_pick_nsplit(B, c->H, c->num_sms, Kr);
 
   // The whole token loop is ONE graph launch: a conditional WHILE node whose body is the captured decode step; the
@@ -1344,7 +1585,7 @@ extern "C" int wl_test_wgemm(wl_ctx* c, const uint16_t* w_f16, const uint16_t* x
     if (mode == 1) WL_CUDA(cudaMemcpy(dout, out, no * 4, cudaMemcpyHostToDevice));
     if (bias) WL_CUDA(cudaMemcpy(db, bias, (size_t)n_out * 4, cudaMemcpyHostToDevice));
     WL_CUDA(cudaDeviceSynchronize());
-    wgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh, (long)no);
+    wgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh, (long)no, dw, (long)nw * 2);
     WL_CUDA(cudaStreamSynchronize(c->st));
     if (mode == 2) {
       std::vector<__half> h(no);

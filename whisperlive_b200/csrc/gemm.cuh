@@ -81,8 +81,9 @@ void dec_gemm_tl_bind(unsigned long long* p);
 // Small-batch decode GEMM with fused epilogue (wgemm.cu, R <= 32 rows, mma.sync + bulk-copied weight slices).
 // mode 0: out_f32 = acc + bias; 1: out_f32 += acc + bias (in place); 2: out_f16 = gelu(acc + bias);
 // 3: out_f32[ks] = raw partial sum of K range ks (only when K > 1280)
+// prefetch_ptr / prefetch_bytes: the weights of the next linear layer, requested into L2 by this launch (optional)
 void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, int R, const float* bias, int mode, float* out_f32,
-           __half* out_f16, long part_stride);
+           __half* out_f16, long part_stride, const void* prefetch_ptr = nullptr, long prefetch_bytes = 0);
 bool wgemm_supported(int R, int K);
 int wgemm_ksplit(int K);
 long wgemm_launch_count();

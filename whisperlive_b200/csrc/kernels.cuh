@@ -36,6 +36,10 @@ struct PartialSrc {
 void prep_features(cudaStream_t st, const float* feats, __half* out, int B, int n_mels);
 // weight upload: fp32 [a][b][k] -> fp16 [a][k][b] (conv kernels; b = k = 1 is a plain cast)
 void cast_weight_f16(cudaStream_t st, const float* in, __half* out, long a, long b, long k);
+// window gather from the resident log-mel of wl_mel_device: feat[w][m][t] = t < len[w] ? mel[off[stream[w]] + m * frames[stream[w]] + seek[w] + t] : 0
+// (the reference slices features[:, seek : seek + segment_size] and zero-pads to 3000 frames on the host: transcriber_faster_whisper.py:1115-1127)
+void gather_windows(cudaStream_t st, const float* mel, const long* mel_off, const int* frames, const int* win_stream, const int* win_seek,
+                    const int* win_len, float* feat, int n_windows, int n_mels);
 // y = LayerNorm(x) * gamma + beta ; x f32 [rows][d] -> y fp16 [rows][d] (and optionally f32 copy)
 void layernorm_rows(cudaStream_t st, const float* x, const float* gamma, const float* beta, __half* y, float* y32,
                     long rows, int d);
@@ -59,6 +63,8 @@ struct DecodeState {
   int* row_done;     // [R]
   int* hist;         // [R][T_MAX] generated tokens
   short* src;        // [R][T_MAX] physical cache row holding position p of this row's sequence
+  int* wrow;         // optional [R]: physical cache row the self-attention kernel WRITES row r's new k/v to (null: r itself;
+                     //   the batched prefill runs every prompt position as its own row, all writing to the stream's first row)
   // per-row candidates produced by search_rows
   float* cand_val;   // [R][MAX_CAND]
   int* cand_tok;     // [R][MAX_CAND]
@@ -135,7 +141,16 @@ void search_streams(cudaStream_t st, const DecodeState& s, const SearchOpts& o, 
 // step budget is not used up (one thread; it runs after search_streams, so n_done is final for this step).
 void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalHandle h, int B);
 
-// initialise the state for a generate call (prompts already uploaded)
-void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R);
+// initialise the state for a generate call (prompts already uploaded).  prefilled = 1: positions 0 .. P-2 of every prompt
+// are already in the self-attention cache (K8 batched prefill): start at the last prompt token.
+void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled = 0);
+
+// ---------------------------------------------------------------------------- K8 batched prefill helpers (prefill.cu)
+void prefill_embed(cudaStream_t st, const int* tok, const int* pos, const int* active, const int* wrow, const __half* emb,
+                   const __half* pos_emb, float* x, short* src, int M, int d);
+void prefill_kv_write(cudaStream_t st, const float* qkv, const int* pos, const int* active, const int* wrow, __half* kc, __half* vc,
+                      long row_stride, int M, int H, int d);
+void gather_rows(cudaStream_t st, const float* x, const int* rows, float* dst, int n, int d);
+void row_prob(cudaStream_t st, const float* logits, int vocab, int vocab_ld, const int* target, const int* out_index, float* out, int n);
 
 }  // namespace wl

@@ -395,6 +395,18 @@ __global__ void __launch_bounds__(128) search_streams_kernel(DecodeState s, Sear
     for (int p = tid; p < len_old; p += 128) sh_hist[j][p] = s.hist[(long)(row0 + j) * T_MAX + p];
     for (int p = tid; p <= pos_old; p += 128) sh_src[j][p] = s.src[(long)(row0 + j) * T_MAX + p];
   }
+  // candidate lists and cumulative scores of the alive rows -> shared memory with one parallel load: the merge below is
+  // one thread walking <= 8 x 16 entries, and as dependent global loads that walk alone was ~12 us of the token step
+  __shared__ float sh_cval[MAX_ROWS_PER_STREAM][MAX_CAND];
+  __shared__ int sh_ctok[MAX_ROWS_PER_STREAM][MAX_CAND];
+  __shared__ float sh_cum[MAX_ROWS_PER_STREAM];
+  for (int i = tid; i < n_alive * MAX_CAND; i += 128) {
+    const int j = i / MAX_CAND, k = i % MAX_CAND;
+    sh_cval[j][k] = s.cand_val[(long)(row0 + j) * MAX_CAND + k];
+    sh_ctok[j][k] = s.cand_tok[(long)(row0 + j) * MAX_CAND + k];
+  }
+  if (tid < n_alive) sh_cum[tid] = s.cum[row0 + tid];
+  __syncthreads();
   if (tid == 0) {
     // merged top-2K over the alive rows (each row's list is sorted): (total desc, row asc, list order)
     int idx[MAX_ROWS_PER_STREAM];
@@ -408,13 +420,13 @@ __global__ void __launch_bounds__(128) search_streams_kernel(DecodeState s, Sear
       float bs = -INFINITY;
       for (int j = 0; j < n_alive; ++j) {
         if (idx[j] >= NC) continue;
-        const float cv = s.cand_val[(long)(row0 + j) * MAX_CAND + idx[j]];
+        const float cv = sh_cval[j][idx[j]];
         if (cv == -INFINITY) continue;
-        const float tot = s.cum[row0 + j] + cv;
+        const float tot = sh_cum[j] + cv;
         if (tot > bs) { bs = tot; bj = j; }
       }
       if (bj < 0) break;
-      cb[nc] = bj; ct[nc] = s.cand_tok[(long)(row0 + bj) * MAX_CAND + idx[bj]]; cs[nc] = bs;
+      cb[nc] = bj; ct[nc] = sh_ctok[bj][idx[bj]]; cs[nc] = bs;
       ++idx[bj]; ++nc;
     }
     int na = 0, nh = 0, hc = s.hyp_count[b];
@@ -509,15 +521,21 @@ void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalH
 }
 
 // ============================================================================ init
-__global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v) {
+__global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v, int prefilled) {
   const int b = blockIdx.x, tid = threadIdx.x;
   const int Kr = o.rows_per_stream, row0 = b * Kr;
   const int P = s.prompt_len[b];
+  // token-by-token feeding starts at prompt position 0; after the batched prefill (positions 0 .. P-2 cached in the
+  // stream's first row) the first decode step feeds the LAST prompt token
+  const int fed0 = (prefilled && s.force_len[b] == 0) ? P - 1 : 0;
+  // independent sampling rows all continue from the prompt cache of row 0 (what search_streams does when the feeding
+  // reaches the last prompt token)
+  const bool fan_out = o.beam == 1 && s.force_len[b] == 0 && fed0 == P - 1;
   if (tid < Kr) {
     const int r = row0 + tid;
-    const bool on = tid == 0 || (P == 1 && o.beam == 1 && s.force_len[b] == 0);
-    s.tok_in[r] = s.prompt[(long)b * T_MAX];
-    s.pos[r] = 0;
+    const bool on = tid == 0 || fan_out;
+    s.tok_in[r] = s.prompt[(long)b * T_MAX + fed0];
+    s.pos[r] = fed0;
     s.active[r] = on ? 1 : 0;
     s.cum[r] = 0.f;
     s.gen_len[r] = 0;
@@ -525,20 +543,24 @@ __global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v) {
     s.row_done[r] = 0;
     s.nospeech_row[r] = 0.f;
   }
+  for (int j = 0; j < Kr; ++j) {
+    if (j > 0 && !fan_out) break;
+    for (int p = tid; p < fed0; p += blockDim.x) s.src[(long)(row0 + j) * T_MAX + p] = (short)row0;
+  }
   if (tid == 0) {
-    s.fed[b] = 0;
+    s.fed[b] = fed0;
     s.step[b] = 0;
     s.done[b] = 0;
     s.n_alive[b] = 1;
-    s.no_speech[b] = 0.f;
+    if (!prefilled) s.no_speech[b] = 0.f;   // the prefill pass zeroes it and, with sot inside the prompt, has already written it
     s.hyp_count[b] = 0;
-    s.steps_run[b] = 0;
+    s.steps_run[b] = fed0;
     if (b == 0) *s.n_done = 0;
   }
 }
 
-void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R) {
-  decode_init_kernel<<<B, 32, 0, st>>>(s, o, v);
+void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled) {
+  decode_init_kernel<<<B, 32, 0, st>>>(s, o, v, prefilled);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

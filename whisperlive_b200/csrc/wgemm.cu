@@ -40,6 +40,8 @@ struct WgemmParams {
   __half* out_f16;     // mode 2: [R][n_out] gelu(acc + bias)
   long part_stride;    // mode 3: elements between K ranges
   int n_out, K, R, nf, kr, ksplit, mode;
+  const void* pf_ptr;  // weights of the NEXT linear layer: every CTA asks L2 for its share (no data dependency) ...
+  long pf_bytes;       // ... so that when that layer's CTAs become resident their slices are L2 hits, not an HBM stream
 };
 
 __device__ __forceinline__ void mma_16816_f32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -77,17 +79,34 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
     mbar_expect_tx(bar, (uint32_t)(nf * kr * 2));
 #pragma unroll 1
     for (int f = 0; f < nf; ++f) bulk_load_1d(sW + f * pitch, p.W + (long)(f0 + f) * p.K + k0, (uint32_t)(kr * 2), bar);
+    if (p.pf_bytes > 0) {
+      // HBM keeps streaming one layer ahead of the dependency chain: the whole layer's weights (46 MB for large-v3) fit
+      // in the 126 MB L2 at the batch sizes this kernel serves
+      const long share = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15L;
+      const long lo = (long)blockIdx.x * share;
+      long left = min(share, p.pf_bytes - lo);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.pf_ptr) + lo;
+#pragma unroll 1
+      while (left > 0) {
+        const uint32_t n = (uint32_t)min(left, 65536L) & ~15u;
+        if (n == 0) break;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
+        src += n;
+        left -= n;
+      }
+    }
   }
-  // epilogue assignment: thread owns elements e = tid + i * 256 of the CTA's [MT*16 rows][nf features] tile.  Their bias
-  // (a weight) is fetched before the dependency wait and the residual right after it, so that the epilogue itself is
-  // shared-memory sums and one store -- no global round trip left at the end of the chain.
-  constexpr int EPI = (MT * 16 * WG_MAX_NF + WG_WARPS * 32 - 1) / (WG_WARPS * 32);
-  const int total = MT * 16 * nf;
-  float ebias[EPI], eres[EPI];
+  // epilogue assignment without divisions: thread (er = tid / 16, fl = tid % 16) owns rows er (+16 with two m-tiles)
+  // and features fl, fl + 16, fl + 32 (< nf) of the CTA's tile.  Their bias (a weight) is fetched before the dependency
+  // wait and the residual right after it, so that the epilogue itself is shared-memory sums and one store each -- no
+  // global round trip left at the end of the chain.
+  constexpr int EF = (WG_MAX_NF + 15) / 16;
+  const int er = tid >> 4, fl = tid & 15;
+  float ebias[EF], eres[MT][EF];
 #pragma unroll
-  for (int i = 0; i < EPI; ++i) {
-    const int e = tid + i * WG_WARPS * 32;
-    ebias[i] = (e < total && p.mode != 3 && p.bias != nullptr) ? __ldg(p.bias + f0 + e % nf) : 0.f;
+  for (int i = 0; i < EF; ++i) {
+    const int f = fl + 16 * i;
+    ebias[i] = (f < nf && p.mode != 3 && p.bias != nullptr) ? __ldg(p.bias + f0 + f) : 0.f;
   }
   tl_stamp(TL_GEMM_PART, 0);
   pdl_wait();
@@ -106,11 +125,12 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
       xa[mt][i][1] = (c < nchunks && r1 < p.R) ? __ldcg(reinterpret_cast<const uint4*>(xp + (long)r1 * p.K)) : z;
     }
 #pragma unroll
-  for (int i = 0; i < EPI; ++i) {
-    const int e = tid + i * WG_WARPS * 32;
-    const int r = e / nf;
-    eres[i] = (p.mode == 1 && e < total && r < p.R) ? __ldcg(p.out_f32 + (long)r * p.n_out + f0 + (e - r * nf)) : 0.f;
-  }
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int i = 0; i < EF; ++i) {
+      const int f = fl + 16 * i, r = mt * 16 + er;
+      eres[mt][i] = (p.mode == 1 && f < nf && r < p.R) ? __ldcg(p.out_f32 + (long)r * p.n_out + f0 + f) : 0.f;
+    }
   mbar_wait(bar, 0);
   const int ntiles = nf >> 3;
 #pragma unroll 1
@@ -140,24 +160,22 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
     }
   }
   __syncthreads();
-  // fixed-order sum over the 8 warps + epilogue: element e = (mt * 16 + row, feature)
+  // fixed-order sum over the 8 warps + epilogue
 #pragma unroll
-  for (int i = 0; i < EPI; ++i) {
-    const int e = tid + i * WG_WARPS * 32;
-    const int r = e / nf, f = e - r * nf;
-    if (e < total && r < p.R) {
-      const float* rp = red + (((f >> 3) * MT + (r >> 4)) * 128) + (r & 15) * 8 + (f & 7);
-      float v = 0.f;
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int w = 0; w < WG_WARPS; ++w) v += rp[w * ntl * MT * 128];
-      v += ebias[i];
-      const long o = (long)r * p.n_out + f0 + f;
-      if (p.mode == 0) p.out_f32[o] = v;
-      else if (p.mode == 1) p.out_f32[o] = eres[i] + v;
-      else if (p.mode == 2) p.out_f16[o] = __float2half_rn(gelu_erf(v));
-      else p.out_f32[(long)ks * p.part_stride + o] = v;
+    for (int i = 0; i < EF; ++i) {
+      const int f = fl + 16 * i, r = mt * 16 + er;
+      if (f < nf && r < p.R) {
+        const float* rp = red + (((f >> 3) * MT + mt) * 128) + er * 8 + (f & 7);
+        float v = ebias[i];
+#pragma unroll
+        for (int w = 0; w < WG_WARPS; ++w) v += rp[w * ntl * MT * 128];
+        const long o = (long)r * p.n_out + f0 + f;
+        if (p.mode == 2) p.out_f16[o] = __float2half_rn(gelu_erf(v));
+        else p.out_f32[(p.mode == 3 ? (long)ks * p.part_stride : 0L) + o] = v + eres[mt][i];
+      }
     }
-  }
 }
 
 static int wg_smem_bytes(int MT, int nf = WG_MAX_NF, int kr = WG_WARPS * WG_CH * 32) {
@@ -180,7 +198,7 @@ int wgemm_ksplit(int K) {
 // mode 0: out_f32 = acc + bias; 1: out_f32 += acc + bias (in place); 2: out_f16 = gelu(acc + bias);
 // 3: out_f32[ks] = raw partial sum of K range ks (K > 1280: the consumer adds the ranges and the bias)
 void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, int R, const float* bias, int mode, float* out_f32,
-           __half* out_f16, long part_stride) {
+           __half* out_f16, long part_stride, const void* prefetch_ptr, long prefetch_bytes) {
   WL_CHECK(wgemm_supported(R, K) && n_out % 8 == 0, WL_ERR_ARG, "wgemm: unsupported problem R=%d n_out=%d K=%d", R, n_out, K);
   const int ksplit = wgemm_ksplit(K);
   WL_CHECK(ksplit == 1 || mode == 3, WL_ERR_ARG, "wgemm: K=%d needs %d K ranges: only the partial-sum epilogue supports that", K, ksplit);
@@ -190,6 +208,8 @@ void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, 
   WgemmParams p;
   p.W = W; p.X = X; p.bias = bias; p.out_f32 = out_f32; p.out_f16 = out_f16; p.part_stride = part_stride;
   p.n_out = n_out; p.K = K; p.R = R; p.ksplit = ksplit; p.mode = mode;
+  static const bool pf_env = [] { const char* e = getenv("WLB200_WPREFETCH"); return e ? atoi(e) != 0 : true; }();
+  p.pf_ptr = prefetch_ptr; p.pf_bytes = (pf_env && prefetch_ptr) ? prefetch_bytes : 0;
   // K range per CTA: equal ranges, multiples of 32
   p.kr = cdiv(cdiv(K, ksplit), 32) * 32;
   // features per CTA: the smallest multiple of 8 (<= 40) for which the grid fits one wave of one CTA per SM; the weight

@@ -242,6 +242,47 @@ class B200Whisper:
                 outs[i0 + j] = out[ooff[j]:ooff[j + 1]].reshape(self.n_mels, f)
         return outs  # type: ignore
 
+    # ------------------------------------------------------------------ resident features (K1 -> K2 without leaving HBM)
+    def mel_device(self, waveforms: Sequence[np.ndarray]) -> List[int]:
+        """log-mel of up to ``max_streams`` waveforms, kept on the device until the next call; returns the frame
+        count of each (len // 160 + 1, the last frame being the one callers drop).  Pair with ``encode_windows``."""
+        chunk = [np.ascontiguousarray(w, dtype=np.float32) for w in waveforms]
+        if not chunk or len(chunk) > self.max_streams:
+            raise ValueError(f"mel_device takes 1..{self.max_streams} waveforms, got {len(chunk)}")
+        if min(len(w) for w in chunk) <= 0:
+            raise ValueError("mel: empty waveform")
+        off = np.zeros(len(chunk) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(w) for w in chunk])
+        pcm = np.concatenate(chunk)
+        frames = np.zeros(len(chunk), dtype=np.int32)
+        with self._lock:
+            rc = self.lib.wl_mel_device(self.ctx, _lib.ptr(pcm, C.c_float), _lib.ptr(off, C.c_int64), len(chunk), _lib.ptr(frames, C.c_int32))
+            _lib.check(self.lib, self.ctx, rc, "wl_mel_device")
+            self._resident_epoch = getattr(self, "_resident_epoch", 0) + 1
+        return [int(f) for f in frames]
+
+    def encode_windows(self, windows: Sequence[Tuple[int, int, int]]) -> EncoderOutput:
+        """Encode windows ``(stream, seek, length)`` cut from the resident log-mel (zero-padded to 3000 frames on the
+        device, what ``pad_or_trim`` does on the host in the reference, transcriber_faster_whisper.py:1127)."""
+        slots_all: List[int] = []
+        with self._lock:
+            free = self.free_slots()
+            if len(windows) > free:
+                raise RuntimeError(f"encode: {len(windows)} windows requested but only {free} encoder slots are free")
+            for b0 in range(0, len(windows), self.max_streams):
+                part = windows[b0:b0 + self.max_streams]
+                arr = np.asarray(part, dtype=np.int32).reshape(-1, 3)
+                st, sk, ln = (np.ascontiguousarray(arr[:, i]) for i in range(3))
+                slots = np.zeros(len(part), dtype=np.int32)
+                rc = self.lib.wl_encode_windows(self.ctx, len(part), _lib.ptr(st, C.c_int32), _lib.ptr(sk, C.c_int32),
+                                                _lib.ptr(ln, C.c_int32), _lib.ptr(slots, C.c_int32))
+                if rc != 0 and slots_all:
+                    a = np.asarray(slots_all, dtype=np.int32)
+                    self.lib.wl_slots_release(self.ctx, _lib.ptr(a, C.c_int32), len(slots_all))
+                _lib.check(self.lib, self.ctx, rc, "wl_encode_windows")
+                slots_all.extend(int(x) for x in slots)
+        return EncoderOutput(_SlotRef(self, slots_all), slots_all, self.dims.d_model)
+
     # ------------------------------------------------------------------ ctranslate2.models.Whisper.encode
     def encode(self, features, to_cpu: bool = False) -> EncoderOutput:
         f = np.ascontiguousarray(np.asarray(features), dtype=np.float32)
@@ -276,8 +317,8 @@ class B200Whisper:
                  no_repeat_ngram_size: int = 0, max_length: int = 448, return_scores: bool = False,
                  return_no_speech_prob: bool = False, max_initial_timestamp_index: int = 50, suppress_blank: bool = True,
                  suppress_tokens: Optional[Sequence[int]] = (-1,), sampling_topk: int = 1, sampling_temperature: float = 1,
-                 seed: Optional[int] = None, max_length_per_stream: Optional[Sequence[int]] = None
-                 ) -> List[WhisperGenerationResult]:
+                 seed: Optional[int] = None, max_length_per_stream: Optional[Sequence[int]] = None,
+                 prefill: Optional[bool] = None) -> List[WhisperGenerationResult]:
         if repetition_penalty != 1 or no_repeat_ngram_size != 0:
             raise NotImplementedError("repetition_penalty / no_repeat_ngram_size other than the reference's 1 / 0")
         if seed is None:
@@ -305,7 +346,8 @@ class B200Whisper:
                 max_initial_timestamp_index=int(max_initial_timestamp_index), sampling_topk=int(sampling_topk),
                 sampling_temperature=float(sampling_temperature), seed=int(seed) & 0xFFFFFFFF,
                 suppress_tokens=_lib.ptr(sup, C.c_int32) if len(sup) else None, n_suppress=len(sup),
-                use_cuda_graph=int(self.use_cuda_graph), max_length_per_stream=None)
+                use_cuda_graph=int(self.use_cuda_graph), max_length_per_stream=None,
+                prefill=0 if prefill is None else (1 if prefill else 2))
             mlps = None
             if max_length_per_stream is not None:
                 mlps = np.asarray(list(max_length_per_stream)[b0:b0 + B], dtype=np.int32)

@@ -21,6 +21,40 @@ def mel_filters(n_mels: int, sr: int = 16000, n_fft: int = 400) -> np.ndarray:
     return fb.astype(np.float32)
 
 
+class ResidentFeatures:
+    """The log-mel of one stream, resident in HBM (engine.mel_device).  Quacks like the ``float32 [n_mels, frames]``
+    array the reference's FeatureExtractor returns as far as the transcriber needs it: ``shape`` and slicing along the
+    frame axis (``f[:, a:b]`` / ``f[..., a:]``), which yields views the engine encodes with ``encode_windows``.
+    ``np.asarray(f)`` is deliberately not supported -- a consumer that needs host values calls the host-returning
+    ``FeatureExtractor.__call__``."""
+
+    ndim = 2
+
+    def __init__(self, engine, stream: int, n_mels: int, start: int, stop: int, epoch: int):
+        self.engine, self.stream, self.n_mels, self.start, self.stop, self.epoch = engine, stream, n_mels, start, stop, epoch
+
+    @property
+    def shape(self):
+        return (self.n_mels, self.stop - self.start)
+
+    def __getitem__(self, key) -> "ResidentFeatures":
+        if not isinstance(key, tuple):
+            key = (key,)
+        sl = key[-1]
+        lead = key[:-1]
+        ok_lead = all(k is Ellipsis or (isinstance(k, slice) and k == slice(None)) for k in lead)
+        if not (isinstance(sl, slice) and sl.step in (None, 1) and ok_lead and len(lead) <= 1):
+            raise TypeError("ResidentFeatures supports slicing along the frame axis only")
+        a, b, _ = sl.indices(self.stop - self.start)
+        return ResidentFeatures(self.engine, self.stream, self.n_mels, self.start + a, self.start + max(a, b), self.epoch)
+
+    def window(self, max_frames: int = 3000):
+        """(stream, seek, length) for engine.encode_windows."""
+        if getattr(self.engine, "_resident_epoch", None) != self.epoch:
+            raise RuntimeError("these features are no longer resident: a later mel_device call replaced them")
+        return (self.stream, self.start, min(self.stop - self.start, max_frames))
+
+
 class FeatureExtractor:
     def __init__(self, engine, feature_size: int = 80, sampling_rate: int = 16000, hop_length: int = 160,
                  chunk_length: int = 30, n_fft: int = 400):
@@ -46,6 +80,14 @@ class FeatureExtractor:
 
     def __call__(self, waveform: np.ndarray, padding: int = 160, chunk_length: Optional[int] = None) -> np.ndarray:
         return self.batch([waveform], padding, chunk_length)[0]
+
+    def batch_resident(self, waveforms: Sequence[np.ndarray], chunk_length: Optional[int] = None) -> List[ResidentFeatures]:
+        """Like ``batch`` but the features stay in HBM (at most ``engine.max_streams`` waveforms per call, valid until
+        the next call): what ``B200WhisperModel.transcribe_batch`` uses between its own mel and encode steps."""
+        self._set_chunk(chunk_length)
+        frames = self.engine.mel_device(waveforms)
+        ep = self.engine._resident_epoch
+        return [ResidentFeatures(self.engine, i, self.feature_size, 0, f, ep) for i, f in enumerate(frames)]
 
     def batch(self, waveforms: Sequence[np.ndarray], padding: int = 160, chunk_length: Optional[int] = None) -> List[np.ndarray]:
         if padding != 160:

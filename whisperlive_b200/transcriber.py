@@ -185,6 +185,8 @@ def restore_speech_timestamps(segments: List[Segment], speech_chunks: List[dict]
 
 
 def pad_or_trim(features: np.ndarray, length: int = 3000) -> np.ndarray:
+    if hasattr(features, "window"):          # resident features: trimmed here, zero-padded on the device by the encoder's gather
+        return features[..., :length]
     n = features.shape[-1]
     if n >= length:
         return features[..., :length]
@@ -552,8 +554,13 @@ class B200WhisperModel:
         if not live:
             return results
         t0 = time.perf_counter()
-        feats = self.feature_extractor.batch([prepared[i]["audio"] for i in live],
-                                             chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
+        fe = self.feature_extractor
+        cap = int(getattr(self.model, "max_streams", 0) or 0)
+        if hasattr(fe, "batch_resident") and 0 < len(live) <= cap:
+            # mel -> encoder without leaving HBM (the reference's two host-side calls, :862 and :1348, fused on the device)
+            feats = fe.batch_resident([prepared[i]["audio"] for i in live], chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
+        else:
+            feats = fe.batch([prepared[i]["audio"] for i in live], chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
         tm["mel"] = time.perf_counter() - t0
         for i, f in zip(live, feats):
             prepared[i]["features"] = f
@@ -751,6 +758,8 @@ class B200WhisperModel:
         np.pad per stream, then np.stack).  The engine consumes the batch before encode() returns, and the buffer is
         per thread, so nothing else can touch it in between."""
         fe = self.feature_extractor
+        if hasattr(views[0], "window"):
+            return [v.window(fe.nb_max_frames) for v in views]      # resident: the device gathers + pads
         n_frames, n_mels = fe.nb_max_frames, views[0].shape[0]
         tls = self.__dict__.setdefault("_win_tls", threading.local())   # one buffer per calling thread: no sharing
         buf = getattr(tls, "buf", None)
@@ -771,7 +780,12 @@ class B200WhisperModel:
         return job.segments
 
     def encode(self, features: np.ndarray):
-        """Reference :1339-1348."""
+        """Reference :1339-1348.  Also takes features resident on the device (one ``ResidentFeatures`` view or the
+        window list ``_stack_windows`` builds from them)."""
+        if hasattr(features, "window"):
+            return self.model.encode_windows([features.window(self.feature_extractor.nb_max_frames)])
+        if isinstance(features, list):
+            return self.model.encode_windows(features)
         if features.ndim == 2:
             features = features[None]
         return self.model.encode(np.ascontiguousarray(features, dtype=np.float32), to_cpu=False)
