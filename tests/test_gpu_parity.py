@@ -489,6 +489,42 @@ def test_slot_pool_accounting():
     assert eng.free_slots() == free0
 
 
+# --------------------------------------------------------------------------------------- N1 weight loading from disk
+@pytest.mark.parametrize("fmt", ["safetensors", "ct2"])
+def test_load_checkpoint_directory_from_disk(tmp_path, fmt):
+    """N1: a model DIRECTORY in either on-disk format the reference's users have -- HF ``model.safetensors``
+    (openai/whisper-*) or the CTranslate2 ``model.bin`` download_model fetches (faster_whisper_backend.py:133-178) --
+    plus tokenizer.json / config.json, through the product constructors (no weights= / engine= injection): the engine
+    built from disk encodes and decodes exactly like the one built from the same tensors in memory."""
+    import json
+    from whisperlive_b200.engine import B200Whisper
+    from whisperlive_b200.transcriber import B200WhisperModel
+    dims = dims_for("micro.en")
+    w = random_init(dims, seed=4)
+    d = tmp_path / "model"
+    d.mkdir()
+    if fmt == "safetensors":
+        from safetensors.torch import save_file
+        save_file({k: v.half().contiguous() for k, v in w.items()}, str(d / "model.safetensors"))
+    else:
+        from whisperlive_b200 import ct2_format
+        ct2_format.save_ct2_model_bin(w, str(d / "model.bin"))
+    heads = [[1, 0], [1, 1]]
+    (d / "config.json").write_text(json.dumps({"alignment_heads": heads}))
+    (d / "preprocessor_config.json").write_text(json.dumps({"feature_size": dims.n_mels, "sampling_rate": 16000, "hop_length": 160,
+                                                            "chunk_length": 30, "n_fft": 400, "processor_class": "ignored"}))
+    build_synthetic_tokenizer(dims.vocab).save(str(d / "tokenizer.json"))
+    eng = B200Whisper.from_model(str(d), max_streams=2, max_beam=5)
+    assert eng.dims.d_model == dims.d_model and eng.dims.vocab == dims.vocab and eng.alignment_heads == [(1, 0), (1, 1)]
+    ref, _ = engine("micro.en", seed=4)
+    feats = np.stack([feats_for(dims, 5.0, 1), feats_for(dims, 8.0, 2)])
+    a, b = np.asarray(eng.encode(feats)), np.asarray(ref.encode(feats))
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    model = B200WhisperModel(str(d), max_streams=2, max_beam=5)          # the call create_model makes (tokenizer.json from the dir)
+    segs, info = model.transcribe(synth.speech_like(6.0, seed=3), beam_size=5, temperature=[0.0], log_prob_threshold=None)
+    assert info.language == "en" and len(segs) > 0 and all(isinstance(s.text, str) for s in segs)
+
+
 # --------------------------------------------------------------------------------------- K13 / K14
 def test_detect_language_matches_oracle():
     eng, orc = engine("micro", seed=1)

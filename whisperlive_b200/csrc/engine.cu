@@ -124,6 +124,12 @@ struct wl_ctx {
     float *x = nullptr, *qkv = nullptr, *qc = nullptr, *xpart = nullptr;
     __half *xn = nullptr, *att = nullptr, *h = nullptr;
     long rows_done = 0, calls = 0;   // statistics
+    // K14 (align through the batched pass)
+    int* row_b = nullptr;
+    long row_b_cap = 0;
+    float *aprobs = nullptr, *mat = nullptr, *tokp = nullptr;
+    int *aT = nullptr, *anf = nullptr, *path = nullptr, *path_len = nullptr;
+    long tokp_cap = 0;
   } pf;
   float* stage_f32 = nullptr;   // wl_load_tensor staging (freed by wl_finalize_weights)
   size_t stage_cap = 0;
@@ -964,38 +970,65 @@ static void prefill_reserve(wl_ctx* c, long rows) {
   f.cap_rows = cap;
 }
 
-// All prompt positions but the last of every stream through the decoder stack in one pass.  hp = prompts [B][T_MAX]
-// (pinned host), P / sot / slots per stream.  Leaves the self-attention cache filled for positions 0 .. P-2 in the
-// stream's first decode row (b * Kr) and the no-speech probability of streams whose sot lies inside the prompt.
-static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* P, const int* sot, const int32_t* slots) {
+namespace wl {
+void gather_align_rows(cudaStream_t st, const float* probs, const int* row_b, const int* row_pos, const int* row_active, float* buf,
+                       const int* heads, int n_heads, int layer, int row0, int n_rows, int H);
+void align_postprocess(cudaStream_t st, float* buf, float* mat, const int* Tn, const int* nfn, int B, int nh, int width, int n_start,
+                       int max_T, int* path_out, int path_cap, int* path_len);
+}
+
+// Row layout of a batched decoder pass: stream b runs positions 0 .. ntok[b]-1 as rows [rowbase[b], rowbase[b] + n8)
+struct PfRows {
+  std::vector<int> tok, pos, act, wrow, vslot, rowbase, row_b;
+  long M = 0;
+  int NV = 0;
+};
+
+static PfRows pf_rows(int B, int Kr, const int* toks, const int* tok_off /*B+1 or null: hp rows of T_MAX*/, const int* ntok,
+                      const int32_t* slots) {
+  PfRows r;
+  r.rowbase.assign(B, 0);
+  for (int b = 0; b < B; ++b) {
+    r.rowbase[b] = (int)r.tok.size();
+    const int n = ntok[b], n8 = (n + 7) / 8 * 8;
+    const int* src = tok_off ? toks + tok_off[b] : toks + (size_t)b * T_MAX;
+    for (int i = 0; i < n8; ++i) {
+      r.tok.push_back(i < n ? src[i] : 0);
+      r.pos.push_back(i < n ? i : 0);
+      r.act.push_back(i < n ? 1 : 0);
+      r.wrow.push_back(b * Kr);
+      r.row_b.push_back(b);
+    }
+    for (int g = 0; g < n8 / 8; ++g) r.vslot.push_back(slots[b]);
+  }
+  r.M = (long)r.tok.size();
+  r.NV = (int)r.vslot.size();
+  return r;
+}
+
+// The decoder stack over M rows (every prompt / teacher-forced position of every stream at once): uploads the row
+// tables, runs embed + Ld layers.  align = true additionally captures the cross-attention probabilities of the
+// alignment heads into c->align_buf [B][nh][T_MAX][1500].  On return f.x holds the final residual stream of every row.
+static void pf_stack(wl_ctx* c, const PfRows& r, bool align) {
   const int d = c->d, H = c->H, ff = 4 * c->d;
   cudaStream_t st = c->st;
-  WL_CUDA(cudaMemsetAsync(c->ds.no_speech, 0, B * sizeof(float), st));
-  std::vector<int> tok, pos, act, wrow, vslot, rowbase(B, 0);
-  for (int b = 0; b < B; ++b) {
-    rowbase[b] = (int)tok.size();
-    const int n = P[b] - 1, n8 = (n + 7) / 8 * 8;
-    for (int i = 0; i < n8; ++i) {
-      tok.push_back(i < n ? hp[(size_t)b * T_MAX + i] : 0);
-      pos.push_back(i < n ? i : 0);
-      act.push_back(i < n ? 1 : 0);
-      wrow.push_back(b * Kr);
-    }
-    for (int g = 0; g < n8 / 8; ++g) vslot.push_back(slots[b]);
-  }
-  const long M = (long)tok.size();
-  if (M == 0) return;
+  const long M = r.M;
+  const int NV = r.NV;
   prefill_reserve(c, M);
   wl_ctx::Prefill& f = c->pf;
-  const int NV = (int)vslot.size();
-  WL_CUDA(cudaMemcpyAsync(f.tok, tok.data(), M * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(f.pos, pos.data(), M * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(f.active, act.data(), M * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(f.wrow, wrow.data(), M * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(f.vslot, vslot.data(), NV * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.tok, r.tok.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.pos, r.pos.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.active, r.act.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.wrow, r.wrow.data(), M * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.vslot, r.vslot.data(), NV * 4, cudaMemcpyHostToDevice, st));
   WL_CUDA(cudaMemsetAsync(f.vdone, 0, NV * 4, st));
+  const int nh = (int)c->align_heads.size() / 2;
+  if (align) {
+    if (!f.row_b_cap || f.row_b_cap < f.cap_rows) { f.row_b = dalloc<int>(c, f.cap_rows); f.row_b_cap = f.cap_rows; }
+    WL_CUDA(cudaMemcpyAsync(f.row_b, r.row_b.data(), M * 4, cudaMemcpyHostToDevice, st));
+    if (!f.aprobs) f.aprobs = dalloc<float>(c, (size_t)PF_VCHUNK * 8 * H * S_ENC, false);
+  }
   prefill_embed(st, f.tok, f.pos, f.active, f.wrow, c->emb, c->pos_dec, f.x, f.src, (int)M, d);
-  WL_CUDA(cudaStreamSynchronize(st));   // the host vectors above go out of scope below
   DecodeState sv = c->ds;
   sv.active = f.active; sv.pos = f.pos; sv.src = f.src; sv.wrow = f.wrow;
   auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
@@ -1023,15 +1056,20 @@ static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* 
       e.out = f.qc; e.out_f32 = 1; e.ldm = d; e.bias = L.b_qc;
       gemm_tn(st, opnd(f.xn, M, d, d), opnd(L.w_qc, d, d, d), (int)M, d, d, e);
     }
+    bool capture = false;
+    if (align)
+      for (int i = 0; i < nh; ++i) capture = capture || c->align_heads[2 * i] == l;
     for (int v0 = 0; v0 < NV; v0 += PF_VCHUNK) {   // groups of 8 rows against their stream's encoder K/V
       const int Bv = std::min(PF_VCHUNK, NV - v0);
       DecodeState sx = c->ds;
       sx.done = f.vdone + v0; sx.slot = f.vslot + v0;
       CrossAttnWorkspace ws;
-      ws.part = f.xpart; ws.probs = nullptr;
-      const int nsp = cross_attn_pick_nsplit(Bv, H, c->num_sms, MAX_ROWS_PER_STREAM);
+      ws.part = f.xpart; ws.probs = capture ? f.aprobs : nullptr;
+      const int nsp = capture ? 1 : cross_attn_pick_nsplit(Bv, H, c->num_sms, MAX_ROWS_PER_STREAM);   // exact probabilities need the whole key range
       decoder_cross_attn(st, sx, plain(f.qc + (long)v0 * 8 * d), c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz,
                          c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz, slot_sz, ws, f.att + (long)v0 * 8 * d, Bv, MAX_ROWS_PER_STREAM, H, d, nsp);
+      if (capture)
+        gather_align_rows(st, f.aprobs, f.row_b, f.pos, f.active, c->align_buf, c->align_heads_dev, nh, l, v0 * 8, Bv * 8, H);
     }
     {
       GemmEpilogue e;
@@ -1050,24 +1088,44 @@ static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* 
       gemm_tn(st, opnd(f.h, M, ff, ff), opnd(L.w_fc2, d, ff, ff), (int)M, d, ff, e);
     }
   }
-  // no-speech probability of the streams whose <|startoftranscript|> lies inside the prefilled part: final LayerNorm +
-  // vocabulary projection of that one row per stream (through the decode step's own kernels), softmax, pick
-  std::vector<int> sel, tgt, oidx;
-  for (int b = 0; b < B; ++b)
-    if (sot[b] >= 0 && sot[b] < P[b] - 1) { sel.push_back(rowbase[b] + sot[b]); tgt.push_back(c->cfg.no_speech); oidx.push_back(b); }
-  const int ns = (int)sel.size();
-  if (ns > 0) {
-    std::vector<int> up(3 * (size_t)ns);
-    for (int i = 0; i < ns; ++i) { up[i] = sel[i]; up[ns + i] = tgt[i]; up[2 * ns + i] = oidx[i]; }
-    WL_CUDA(cudaMemcpyAsync(f.sel, up.data(), up.size() * 4, cudaMemcpyHostToDevice, st));
-    gather_rows(st, f.x, f.sel, c->dx, ns, d);
-    layernorm_update_rows(st, c->dx, PartialSrc(), c->lnf_g, c->lnf_b, c->dxn, ns, d);
-    dec_gemm(st, c->emb, c->V, d, c->dxn, ns, c->logits, c->Vld, 0, 1);
-    row_prob(st, c->logits, c->V, c->Vld, f.sel + ns, f.sel + 2 * ns, c->ds.no_speech, ns);
-    WL_CUDA(cudaStreamSynchronize(st));
-  }
+  WL_CUDA(cudaStreamSynchronize(st));   // the row tables of `r` were uploaded asynchronously
   f.rows_done += M;
   f.calls += 1;
+}
+
+// softmax(logits of row sel[j])[tgt[j]] -> out[oidx[j]] for n selected rows of f.x: final LayerNorm + vocabulary
+// projection through the decode step's own kernels, Rm rows at a time
+static void pf_row_probs(wl_ctx* c, const std::vector<int>& sel, const std::vector<int>& tgt, const std::vector<int>& oidx, float* out_dev) {
+  cudaStream_t st = c->st;
+  wl_ctx::Prefill& f = c->pf;
+  const int n = (int)sel.size(), d = c->d;
+  for (int i0 = 0; i0 < n; i0 += c->Rm) {
+    const int m = std::min(c->Rm, n - i0);
+    std::vector<int> up(3 * (size_t)m);
+    for (int i = 0; i < m; ++i) { up[i] = sel[i0 + i]; up[m + i] = tgt[i0 + i]; up[2 * m + i] = oidx[i0 + i]; }
+    WL_CUDA(cudaMemcpyAsync(f.sel, up.data(), up.size() * 4, cudaMemcpyHostToDevice, st));
+    gather_rows(st, f.x, f.sel, c->dx, m, d);
+    layernorm_update_rows(st, c->dx, PartialSrc(), c->lnf_g, c->lnf_b, c->dxn, m, d);
+    dec_gemm(st, c->emb, c->V, d, c->dxn, m, c->logits, c->Vld, 0, 1);
+    row_prob(st, c->logits, c->V, c->Vld, f.sel + m, f.sel + 2 * m, out_dev, m);
+    WL_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+// K8: all prompt positions but the last of every stream through the decoder stack in one pass.  hp = prompts [B][T_MAX]
+// (pinned host), P / sot / slots per stream.  Leaves the self-attention cache filled for positions 0 .. P-2 in the
+// stream's first decode row (b * Kr) and the no-speech probability of streams whose sot lies inside the prompt.
+static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* P, const int* sot, const int32_t* slots) {
+  WL_CUDA(cudaMemsetAsync(c->ds.no_speech, 0, B * sizeof(float), c->st));
+  std::vector<int> ntok(B);
+  for (int b = 0; b < B; ++b) ntok[b] = P[b] - 1;
+  const PfRows r = pf_rows(B, Kr, hp, nullptr, ntok.data(), slots);
+  if (r.M == 0) return;
+  pf_stack(c, r, false);
+  std::vector<int> sel, tgt, oidx;
+  for (int b = 0; b < B; ++b)
+    if (sot[b] >= 0 && sot[b] < P[b] - 1) { sel.push_back(r.rowbase[b] + sot[b]); tgt.push_back(c->cfg.no_speech); oidx.push_back(b); }
+  if (!sel.empty()) pf_row_probs(c, sel, tgt, oidx, c->ds.no_speech);
 }
 
 static VocabIds vocab_ids(wl_ctx* c) {
@@ -1401,52 +1459,6 @@ extern "C" int wl_detect_language(wl_ctx* c, const int32_t* slots, int32_t B, fl
 }
 
 // ------------------------------------------------------------------------------------------ K14 align
-static void median_filter_row(const float* in, float* out, int n, int width) {
-  const int pad = width / 2;
-  if (pad == 0 || n <= pad) { memcpy(out, in, n * sizeof(float)); return; }
-  std::vector<float> w(width);
-  for (int i = 0; i < n; ++i) {
-    for (int k = -pad; k <= pad; ++k) {
-      int j = i + k;
-      if (j < 0) j = -j;
-      if (j >= n) j = 2 * (n - 1) - j;
-      w[k + pad] = in[j];
-    }
-    std::nth_element(w.begin(), w.begin() + pad, w.end());
-    out[i] = w[pad];
-  }
-}
-
-static void dtw_path(const std::vector<float>& cost, int n, int m, std::vector<std::pair<int, int>>& path) {
-  std::vector<float> acc((size_t)(n + 1) * (m + 1), INFINITY);
-  std::vector<signed char> mv((size_t)(n + 1) * (m + 1), -1);
-  auto A = [&](int i, int j) -> float& { return acc[(size_t)i * (m + 1) + j]; };
-  auto Mv = [&](int i, int j) -> signed char& { return mv[(size_t)i * (m + 1) + j]; };
-  A(0, 0) = 0.f;
-  for (int j = 1; j <= m; ++j)
-    for (int i = 1; i <= n; ++i) {
-      const float c0 = A(i - 1, j - 1), c1 = A(i - 1, j), c2 = A(i, j - 1);
-      float cc; signed char t;
-      if (c0 < c1 && c0 < c2) { cc = c0; t = 0; }
-      else if (c1 < c0 && c1 < c2) { cc = c1; t = 1; }
-      else { cc = c2; t = 2; }
-      A(i, j) = cost[(size_t)(i - 1) * m + (j - 1)] + cc;
-      Mv(i, j) = t;
-    }
-  for (int j = 0; j <= m; ++j) Mv(0, j) = 2;
-  for (int i = 0; i <= n; ++i) Mv(i, 0) = 1;
-  int i = n, j = m;
-  path.clear();
-  while (i > 0 || j > 0) {
-    path.emplace_back(i - 1, j - 1);
-    const signed char t = Mv(i, j);
-    if (t == 0) { --i; --j; }
-    else if (t == 1) --i;
-    else --j;
-  }
-  std::reverse(path.begin(), path.end());
-}
-
 extern "C" int wl_align(wl_ctx* c, const int32_t* slots, int32_t B, const int32_t* start_seq, int32_t n_start, const int32_t* text,
                         const int32_t* text_off, const int32_t* num_frames, int32_t median_width, int32_t* pairs_out,
                         int32_t cap_pairs, int32_t* pair_off, float* tok_probs) {
@@ -1469,53 +1481,64 @@ extern "C" int wl_align(wl_ctx* c, const int32_t* slots, int32_t B, const int32_
     maxT = std::max(maxT, off[b + 1] - off[b]);
   }
   WL_CHECK(maxT <= T_MAX, WL_ERR_ARG, "wl_align: sequence of %d tokens exceeds %d", maxT, T_MAX);
-  if (!c->align_probs) c->align_probs = dalloc<float>(c, (size_t)c->Rm * c->H * S_ENC);
   const long need_buf = (long)B * nh * T_MAX * S_ENC;
   if (need_buf > c->align_buf_cap) {
     c->align_buf = dalloc<float>(c, need_buf, false);
     c->align_buf_cap = need_buf;
   }
-  forced_run(c, slots, B, toks.data(), off.data(), true, nullptr, base);
-  std::vector<float> fprob((size_t)B * T_MAX);
-  WL_CUDA(cudaMemcpy(fprob.data(), c->ds.force_prob, fprob.size() * 4, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < B; ++b)
+    WL_CHECK(slots[b] >= 0 && slots[b] < c->NS && c->slot_used[slots[b]], WL_ERR_ARG, "wl_align: stream %d: bad encoder slot %d", b, slots[b]);
+  // ---- teacher-forced pass: every position of every stream at once (the K8 machinery), attention probabilities of
+  // the alignment heads captured on the way
+  std::vector<int> ntok(B);
+  for (int b = 0; b < B; ++b) ntok[b] = off[b + 1] - off[b];
+  const PfRows r = pf_rows(B, 1, toks.data(), off.data(), ntok.data(), slots);
+  pf_stack(c, r, true);
+  wl_ctx::Prefill& f = c->pf;
+  cudaStream_t st = c->st;
+  // ---- P(text token | prefix): the logits row that predicts it
+  const int n_text = text_off[B] - text_off[0];
+  if (n_text > 0) {
+    if (n_text > f.tokp_cap) { f.tokp = dalloc<float>(c, (size_t)n_text + 256); f.tokp_cap = n_text + 256; }
+    std::vector<int> sel, tgt, oidx;
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < text_off[b + 1] - text_off[b]; ++i) {
+        sel.push_back(r.rowbase[b] + n_start + i);
+        tgt.push_back(toks[off[b] + n_start + 1 + i]);
+        oidx.push_back(text_off[b] - text_off[0] + i);
+      }
+    pf_row_probs(c, sel, tgt, oidx, f.tokp);
+    WL_CUDA(cudaMemcpy(tok_probs + text_off[0], f.tokp, (size_t)n_text * 4, cudaMemcpyDeviceToHost));
+  }
+  // ---- standardise / median filter / mean over heads / DTW on the device
+  if (!f.mat) {
+    f.mat = dalloc<float>(c, (size_t)c->Bm * T_MAX * S_ENC, false);
+    f.aT = dalloc<int>(c, c->Bm); f.anf = dalloc<int>(c, c->Bm);
+    f.path = dalloc<int>(c, (size_t)c->Bm * (T_MAX + S_ENC + 2) * 2, false);
+    f.path_len = dalloc<int>(c, c->Bm);
+  }
+  const int path_cap = T_MAX + S_ENC + 2;
+  std::vector<int> hT(B), hnf(B);
+  for (int b = 0; b < B; ++b) {
+    hT[b] = ntok[b];
+    hnf[b] = std::max(1, std::min(num_frames[b] / 2, (int)S_ENC));
+  }
+  WL_CUDA(cudaMemcpyAsync(f.aT, hT.data(), B * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(f.anf, hnf.data(), B * 4, cudaMemcpyHostToDevice, st));
+  align_postprocess(st, c->align_buf, f.mat, f.aT, f.anf, B, nh, median_width, n_start, maxT, f.path, path_cap, f.path_len);
+  std::vector<int> hlen(B), hpath((size_t)B * path_cap * 2);
+  WL_CUDA(cudaMemcpyAsync(hlen.data(), f.path_len, B * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(hpath.data(), f.path, hpath.size() * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaStreamSynchronize(st));
   int np_total = 0;
   pair_off[0] = 0;
   for (int b = 0; b < B; ++b) {
-    const int T = off[b + 1] - off[b], nt = text_off[b + 1] - text_off[b];
-    const int nf = std::max(1, std::min(num_frames[b] / 2, (int)S_ENC));
-    for (int i = 0; i < nt; ++i) tok_probs[text_off[b] + i] = fprob[(size_t)b * T_MAX + n_start + i];
-    // W[h][t][f]: standardise over tokens, median filter over time, mean over heads
-    std::vector<float> W((size_t)nh * T * nf), row(S_ENC), tmp(nf), outr(nf);
-    for (int h = 0; h < nh; ++h)
-      for (int t = 0; t < T; ++t) {
-        WL_CUDA(cudaMemcpy(row.data(), c->align_buf + (((long)b * nh + h) * T_MAX + t) * S_ENC, nf * 4, cudaMemcpyDeviceToHost));
-        memcpy(&W[((size_t)h * T + t) * nf], row.data(), nf * 4);
-      }
-    std::vector<float> mat((size_t)T * nf, 0.f);
-    for (int h = 0; h < nh; ++h) {
-      for (int f = 0; f < nf; ++f) {
-        double mean = 0, var = 0;
-        for (int t = 0; t < T; ++t) mean += W[((size_t)h * T + t) * nf + f];
-        mean /= T;
-        for (int t = 0; t < T; ++t) { const double dlt = W[((size_t)h * T + t) * nf + f] - mean; var += dlt * dlt; }
-        const float sd = (float)sqrt(var / T);
-        for (int t = 0; t < T; ++t) W[((size_t)h * T + t) * nf + f] = (float)((W[((size_t)h * T + t) * nf + f] - mean) / sd);
-      }
-      for (int t = 0; t < T; ++t) {
-        median_filter_row(&W[((size_t)h * T + t) * nf], outr.data(), nf, median_width);
-        for (int f = 0; f < nf; ++f) mat[(size_t)t * nf + f] += outr[f] / nh;
-      }
-    }
-    const int n_rows = T - 1 - n_start;  // rows [n_start, T-1)
-    std::vector<float> cost((size_t)n_rows * nf);
-    for (int t = 0; t < n_rows; ++t)
-      for (int f = 0; f < nf; ++f) cost[(size_t)t * nf + f] = -mat[(size_t)(t + n_start) * nf + f];
-    std::vector<std::pair<int, int>> path;
-    dtw_path(cost, n_rows, nf, path);
-    WL_CHECK(np_total + (int)path.size() <= cap_pairs, WL_ERR_ARG, "wl_align: pairs_out capacity %d too small", cap_pairs);
-    for (auto& p : path) {
-      pairs_out[2 * np_total] = p.first;
-      pairs_out[2 * np_total + 1] = p.second;
+    const int len = hlen[b];
+    WL_CHECK(np_total + len <= cap_pairs, WL_ERR_ARG, "wl_align: pairs_out capacity %d too small", cap_pairs);
+    const int* pp = hpath.data() + (size_t)b * path_cap * 2;
+    for (int k = len - 1; k >= 0; --k) {   // the device wrote the path end -> start
+      pairs_out[2 * np_total] = pp[2 * k];
+      pairs_out[2 * np_total + 1] = pp[2 * k + 1];
       ++np_total;
     }
     pair_off[b + 1] = np_total;

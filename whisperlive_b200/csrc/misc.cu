@@ -39,4 +39,23 @@ void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* prob
   note_launch(1);
 }
 
+// batched pass (K8 machinery): rows of a cross-attention chunk -> align_buf[b][head slot][pos][1500]
+__global__ void gather_align_rows_kernel(const float* __restrict__ probs, const int* __restrict__ row_b, const int* __restrict__ row_pos,
+                                         const int* __restrict__ row_active, float* __restrict__ buf, const int* __restrict__ heads,
+                                         int n_heads, int layer, int row0, int H) {
+  const int i = blockIdx.x, rl = blockIdx.y, r = row0 + rl;
+  if (heads[2 * i] != layer || !row_active[r]) return;
+  const int h = heads[2 * i + 1];
+  const float* src = probs + ((long)rl * H + h) * S_ENC;
+  float* dst = buf + (((long)row_b[r] * n_heads + i) * T_MAX + row_pos[r]) * S_ENC;
+  for (int k = threadIdx.x; k < S_ENC; k += blockDim.x) dst[k] = src[k];
+}
+void gather_align_rows(cudaStream_t st, const float* probs, const int* row_b, const int* row_pos, const int* row_active, float* buf,
+                       const int* heads, int n_heads, int layer, int row0, int n_rows, int H) {
+  dim3 grid(n_heads, n_rows);
+  gather_align_rows_kernel<<<grid, 256, 0, st>>>(probs, row_b, row_pos, row_active, buf, heads, n_heads, layer, row0, H);
+  WL_CUDA(cudaGetLastError());
+  note_launch(1);
+}
+
 }  // namespace wl

@@ -108,3 +108,155 @@ void row_prob(cudaStream_t st, const float* logits, int vocab, int vocab_ld, con
 }
 
 }  // namespace wl
+
+// ============================================================================ K14 alignment post-processing on the device
+// Input: the cross-attention probabilities of the model's alignment heads, W[b][h][t][f] (t < T_b tokens of the
+// teacher-forced sequence, f < nf_b = num_frames/2 encoder positions).  Pipeline (OpenAI whisper/timing.py, ported by
+// CTranslate2; reference call site transcriber_faster_whisper.py:1657-1663): standardise over the token axis -> median
+// filter (reflect padding) along time -> mean over heads -> drop the start-sequence rows and the eot row -> DTW on the
+// negated matrix -> (text index, time index) path.  Round 1 did all of this on one host thread after B*nh*T blocking
+// row copies; here it is three kernels and one small copy of the path.
+namespace wl {
+
+__global__ void __launch_bounds__(128) align_standardize_kernel(float* __restrict__ buf, const int* __restrict__ Tn,
+                                                                const int* __restrict__ nfn, int nh) {
+  const int b = blockIdx.z, h = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
+  const int T = Tn[b], nf = nfn[b];
+  if (f >= nf) return;
+  float* col = buf + (((long)b * nh + h) * T_MAX) * S_ENC + f;
+  double mean = 0.0;
+  for (int t = 0; t < T; ++t) mean += col[(long)t * S_ENC];
+  mean /= T;
+  double var = 0.0;
+  for (int t = 0; t < T; ++t) { const double dl = col[(long)t * S_ENC] - mean; var += dl * dl; }
+  const float sd = (float)sqrt(var / T);
+  for (int t = 0; t < T; ++t) col[(long)t * S_ENC] = (float)((col[(long)t * S_ENC] - mean) / sd);
+}
+
+// mat[b][t][f] = mean over heads of median_width(W[b][h][t][f-pad .. f+pad]) (reflect at the ends of [0, nf))
+__global__ void __launch_bounds__(128) align_median_mean_kernel(const float* __restrict__ buf, float* __restrict__ mat,
+                                                                const int* __restrict__ Tn, const int* __restrict__ nfn, int nh,
+                                                                int width) {
+  const int b = blockIdx.z, t = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
+  const int T = Tn[b], nf = nfn[b];
+  if (t >= T || f >= nf) return;
+  const int pad = width / 2;
+  float acc = 0.f;
+  for (int h = 0; h < nh; ++h) {
+    const float* row = buf + ((((long)b * nh + h) * T_MAX) + t) * S_ENC;
+    float med;
+    if (pad == 0 || nf <= pad) {
+      med = row[f];
+    } else {
+      float w[16];
+      for (int k = -pad; k <= pad; ++k) {
+        int j = f + k;
+        if (j < 0) j = -j;
+        if (j >= nf) j = 2 * (nf - 1) - j;
+        w[k + pad] = row[j];
+      }
+      // selection of the pad-th smallest (what nth_element returns): partial selection sort, width <= 15
+      for (int i = 0; i <= pad; ++i) {
+        int mi = i;
+        for (int j = i + 1; j < width; ++j) mi = w[j] < w[mi] ? j : mi;
+        const float tmp = w[i]; w[i] = w[mi]; w[mi] = tmp;
+      }
+      med = w[pad];
+    }
+    acc += med / nh;
+  }
+  mat[((long)b * T_MAX + t) * S_ENC + f] = acc;
+}
+
+// One CTA per stream: anti-diagonal wavefront over the (n+1) x (m+1) accumulated-cost table (n = T - 1 - n_start text
+// rows incl. <|notimestamps|>, m = nf frames; one thread per row, n + 1 <= 448 <= 512), three diagonals of it in shared
+// memory, the moves packed 2 bits per cell in shared memory (<= 168 KB), then the backtrace by one thread.  Tie rule of the host version it replaces (and of the
+// oracle): diagonal only if strictly smaller than both, else up (text) only if strictly smaller than both, else left.
+// path_out[b][.] receives the path REVERSED (end -> start), path_len[b] its length.
+__global__ void __launch_bounds__(512) align_dtw_kernel(const float* __restrict__ mat, const int* __restrict__ Tn,
+                                                        const int* __restrict__ nfn, int n_start, int* __restrict__ path_out,
+                                                        int path_cap, int* __restrict__ path_len) {
+  extern __shared__ unsigned dtw_smem[];
+  const int b = blockIdx.x, i = threadIdx.x;
+  const int n = Tn[b] - 1 - n_start, m = nfn[b];
+  float* A0 = reinterpret_cast<float*>(dtw_smem);       // diagonal k-2, indexed by i
+  float* A1 = A0 + (T_MAX + 1);                          // diagonal k-1
+  float* A2 = A1 + (T_MAX + 1);                          // diagonal k
+  unsigned* mv = reinterpret_cast<unsigned*>(A2 + (T_MAX + 1));   // [(n+1) * (m+1)] 2-bit moves
+  if (n <= 0 || m <= 0) { if (i == 0) path_len[b] = 0; return; }
+  const long words = ((long)(n + 1) * (m + 1) + 15) / 16;
+  for (long w = i; w < words; w += 512) mv[w] = 0u;
+  for (int q = i; q <= n; q += 512) { A0[q] = INFINITY; A1[q] = INFINITY; A2[q] = INFINITY; }
+  __syncthreads();
+  if (i == 0) A1[0] = 0.f;   // diagonal 0 = cell (0,0); "diagonal -1" (A0) is all inf
+  // cost(i-1, j-1) = -mat[n_start + i - 1][j - 1]; this thread walks row i-1 left to right, 8 columns prefetched
+  const bool has_row = i >= 1 && i <= n;
+  const float* crow = mat + ((long)b * T_MAX + n_start + (has_row ? i - 1 : 0)) * S_ENC;
+  float r[8];
+  {
+    const int j0 = 1 - i;   // column of this thread on diagonal k = 1 (loop starts at k = 1)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int j = j0 + q; r[q] = (has_row && j >= 1 && j <= m) ? -crow[j - 1] : 0.f; }
+  }
+  __syncthreads();
+  for (int k = 1; k <= n + m; ++k) {
+    // diagonal k-1 is in A1 (k = 1: only cell (0,0)); cells (i, j = k - i) of diagonal k
+    const int j = k - i;
+    float v = INFINITY;
+    if (has_row && j >= 1 && j <= m) {
+      const float c0 = A0[i - 1], c1 = A1[i - 1], c2 = A1[i];
+      float cc; unsigned mvv;
+      if (c0 < c1 && c0 < c2) { cc = c0; mvv = 0u; }
+      else if (c1 < c0 && c1 < c2) { cc = c1; mvv = 1u; }
+      else { cc = c2; mvv = 2u; }
+      v = r[0] + cc;
+      const long cell = (long)i * (m + 1) + j;
+      atomicOr(&mv[cell >> 4], mvv << ((cell & 15) * 2));   // (two cells of one diagonal share a word only when m < 16)
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) r[q] = r[q + 1];
+    { const int jn = j + 8; r[7] = (has_row && jn >= 1 && jn <= m) ? -crow[jn - 1] : 0.f; }
+    if (i <= n) A2[i] = v;
+    __syncthreads();
+    float* t = A0; A0 = A1; A1 = A2; A2 = t;
+    // k == 1 special case: A0 must hold diagonal 0 = {(0,0)=0}, A1 diagonal 1 -- that is what the rotation gives
+  }
+  if (i == 0) {
+    int ii = n, jj = m, len = 0;
+    int* out = path_out + (long)b * path_cap * 2;
+    while ((ii > 0 || jj > 0) && len < path_cap) {
+      out[2 * len] = ii - 1; out[2 * len + 1] = jj - 1;
+      ++len;
+      unsigned t2;
+      if (ii == 0) t2 = 2u;
+      else if (jj == 0) t2 = 1u;
+      else { const long cell = (long)ii * (m + 1) + jj; t2 = (mv[cell >> 4] >> ((cell & 15) * 2)) & 3u; }
+      if (t2 == 0u) { --ii; --jj; }
+      else if (t2 == 1u) --ii;
+      else --jj;
+    }
+    path_len[b] = len;
+  }
+}
+
+void align_postprocess(cudaStream_t st, float* buf, float* mat, const int* Tn, const int* nfn, int B, int nh, int width, int n_start,
+                       int max_T, int* path_out, int path_cap, int* path_len) {
+  WL_CHECK(width >= 1 && width <= 15 && (width & 1), WL_ERR_ARG, "align: median filter width %d must be odd and <= 15", width);
+  dim3 g1(cdiv(S_ENC, 128), nh, B);
+  align_standardize_kernel<<<g1, 128, 0, st>>>(buf, Tn, nfn, nh);
+  WL_CUDA(cudaGetLastError());
+  dim3 g2(cdiv(S_ENC, 128), max_T, B);
+  align_median_mean_kernel<<<g2, 128, 0, st>>>(buf, mat, Tn, nfn, nh, width);
+  WL_CUDA(cudaGetLastError());
+  const size_t smem = 3 * (T_MAX + 1) * sizeof(float) + (((size_t)(T_MAX + 1) * (S_ENC + 1) + 15) / 16) * sizeof(unsigned) + 64;
+  static bool primed = false;
+  if (!primed) {
+    WL_CUDA(cudaFuncSetAttribute(align_dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    primed = true;
+  }
+  align_dtw_kernel<<<B, 512, smem, st>>>(mat, Tn, nfn, n_start, path_out, path_cap, path_len);
+  WL_CUDA(cudaGetLastError());
+  note_launch(3);
+}
+
+}  // namespace wl

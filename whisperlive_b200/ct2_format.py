@@ -199,6 +199,31 @@ def load_ct2_model_bin(path: str) -> Dict[str, torch.Tensor]:
     return out
 
 
+def expected_ct2_names(n_enc: int, n_dec: int) -> List[str]:
+    """Every variable name ``load_ct2_model_bin`` reads for a Whisper with n_enc / n_dec layers -- compared against the
+    variable table of a REAL converted model by tests/test_ct2_capture.py (the container layout and these names are
+    restated from memory; that test is what validates them)."""
+    names = ["encoder/conv1/weight", "encoder/conv1/bias", "encoder/conv2/weight", "encoder/conv2/bias",
+             "encoder/position_encodings/encodings", "encoder/layer_norm/gamma", "encoder/layer_norm/beta",
+             "decoder/embeddings/weight", "decoder/position_encodings/encodings", "decoder/layer_norm/gamma", "decoder/layer_norm/beta"]
+
+    def norm(p):
+        return [f"{p}/gamma", f"{p}/beta"]
+
+    def lin(p, i):
+        return [f"{p}/linear_{i}/weight", f"{p}/linear_{i}/bias"]
+    for l in range(n_enc):
+        s_ = f"encoder/layer_{l}"
+        names += norm(f"{s_}/self_attention/layer_norm") + lin(f"{s_}/self_attention", 0) + lin(f"{s_}/self_attention", 1)
+        names += norm(f"{s_}/ffn/layer_norm") + lin(f"{s_}/ffn", 0) + lin(f"{s_}/ffn", 1)
+    for l in range(n_dec):
+        s_ = f"decoder/layer_{l}"
+        names += norm(f"{s_}/self_attention/layer_norm") + lin(f"{s_}/self_attention", 0) + lin(f"{s_}/self_attention", 1)
+        names += norm(f"{s_}/attention/layer_norm") + lin(f"{s_}/attention", 0) + lin(f"{s_}/attention", 1) + lin(f"{s_}/attention", 2)
+        names += norm(f"{s_}/ffn/layer_norm") + lin(f"{s_}/ffn", 0) + lin(f"{s_}/ffn", 1)
+    return names
+
+
 def save_ct2_model_bin(weights: Dict[str, torch.Tensor], path: str, dtype=np.float16) -> None:
     """Inverse of load_ct2_model_bin (tests, and to hand a checkpoint to a CTranslate2 install for cross-checks)."""
     def npy(name):

@@ -355,15 +355,29 @@ class _StreamJob:
             tokenizer=self.tok, tokens=self.decoded.result.sequences_ids[0], time_offset=self.time_offset,
             segment_size=self.segment_size, segment_duration=self.segment_duration, seek=self.seek)
 
+    def alignment_request(self) -> Optional[List[int]]:
+        """Text tokens this window wants aligned (after the timestamp split), or None.  Lets the scheduler run ONE
+        batched ``align`` for all streams of a window instead of one teacher-forced pass per stream."""
+        if not self.needs_alignment():
+            return None
+        self.split()
+        self._presplit = True
+        return [t for sub in self.current for t in sub["tokens"] if t < self.tok.eot]
+
     def finish_window(self) -> None:
         o, d, m = self.opt, self.decoded, self.m
         if self._skip_as_silence():
             self.seek += self.segment_size
             return
-        self.split()
+        if not getattr(self, "_presplit", False):
+            self.split()
+        self._presplit = False
         if o.word_timestamps:
+            pre = getattr(self, "_align_result", None)
+            self._align_result = None
             m.add_word_timestamps([self.current], self.tok, self.enc, self.segment_size, o.prepend_punctuations,
-                                  o.append_punctuations, last_speech_timestamp=self.last_speech_timestamp)
+                                  o.append_punctuations, last_speech_timestamp=self.last_speech_timestamp,
+                                  precomputed=None if pre is None else [pre])
             if not self.single_ts_ending:
                 last_end = get_end(self.current)
                 if last_end is not None and last_end > self.time_offset:
@@ -733,7 +747,7 @@ class B200WhisperModel:
                     tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
                 pending = sorted(nxt)
             t0 = time.perf_counter()
-            self._align_windows([j for j, _ in live])
+            self._align_windows([j for j, _ in live], enc)
             for j, _ in live:
                 j.finish_window()
                 if j.single_window:
@@ -747,10 +761,25 @@ class B200WhisperModel:
                 release()                         # encoder slots back to the pool NOW (explicit, not refcount-driven)
             del enc
 
-    def _align_windows(self, jobs: List[_StreamJob]) -> None:
-        """Hook: batched word alignment of all streams of a window (K14).  The per-stream call inside
-        ``finish_window`` remains the fallback."""
-        return
+    def _align_windows(self, jobs: List[_StreamJob], enc) -> None:
+        """K14 batched: ONE ``align`` call (one teacher-forced pass over all positions of all streams, DTW on the device)
+        for every stream of the window that wants word timestamps -- the reference aligns stream by stream
+        (:1230, :1657-1663).  Streams are grouped by sot sequence (language / task), which ``align`` takes once per call.
+        The per-stream call inside ``finish_window`` remains the fallback for engines without ``select``."""
+        if not hasattr(enc, "select"):
+            return
+        groups: Dict[Tuple[int, ...], List[Tuple[int, _StreamJob, List[int]]]] = {}
+        for k, j in enumerate(jobs):
+            if not j.opt.word_timestamps:
+                continue
+            toks = j.alignment_request()
+            if toks is not None:
+                groups.setdefault(tuple(j.tok.sot_sequence), []).append((k, j, toks))
+        for sot_seq, items in groups.items():
+            res = self.model.align(enc.select([k for k, _, _ in items]), list(sot_seq), [t for _, _, t in items],
+                                   [j.segment_size for _, j, _ in items], median_filter_width=7)
+            for (_, j, _), r in zip(items, res):
+                j._align_result = r
 
     def _stack_windows(self, views: List[np.ndarray]) -> np.ndarray:
         """[B, n_mels, 3000] batch of zero-padded windows, written straight into a buffer that is reused from call to
@@ -860,12 +889,13 @@ class B200WhisperModel:
 
     # -- word timestamps (K14 host part; reference :1515-1714) ------------------------------------
     def add_word_timestamps(self, segments: List[List[dict]], tokenizer: Tokenizer, encoder_output, num_frames: int,
-                            prepend_punctuations: str, append_punctuations: str, last_speech_timestamp: float):
+                            prepend_punctuations: str, append_punctuations: str, last_speech_timestamp: float,
+                            precomputed=None):
         if len(segments) == 0:
             return
         per_seg_tokens = [[[t for t in sub["tokens"] if t < tokenizer.eot] for sub in seg] for seg in segments]
         text_tokens = [list(itertools.chain.from_iterable(x)) for x in per_seg_tokens]
-        alignments = self.find_alignment(tokenizer, text_tokens, encoder_output, num_frames)
+        alignments = self.find_alignment(tokenizer, text_tokens, encoder_output, num_frames, results=precomputed)
         limits = []
         for al in alignments:
             durs = np.array([w["end"] - w["start"] for w in al])
@@ -920,11 +950,12 @@ class B200WhisperModel:
         return last_speech_timestamp
 
     def find_alignment(self, tokenizer: Tokenizer, text_tokens: List[List[int]], encoder_output, num_frames: int,
-                       median_filter_width: int = 7) -> List[List[dict]]:
+                       median_filter_width: int = 7, results=None) -> List[List[dict]]:
         if len(text_tokens) == 0:
             return []
-        results = self.model.align(encoder_output, tokenizer.sot_sequence, text_tokens, num_frames,
-                                   median_filter_width=median_filter_width)
+        if results is None:   # (the batched scheduler path hands in the engine results of its one align call)
+            results = self.model.align(encoder_output, tokenizer.sot_sequence, text_tokens, num_frames,
+                                       median_filter_width=median_filter_width)
         out = []
         for res, toks in zip(results, text_tokens):
             words, word_tokens = tokenizer.split_to_word_tokens(toks + [tokenizer.eot])
