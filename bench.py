@@ -309,8 +309,13 @@ def main():
     res_total, t_e2e = float(stats[0]), float(stats[1])
     value = audio_sec_total * args.steps / res_total
     e2e_value = audio_sec_total * args.steps / t_e2e
-    h2d = sum(w.nbytes for w in my_waves) + n_local * dims.n_mels * 3000 * 4
-    d2h = sum((len(w) // 160 + 1) * dims.n_mels * 4 for w in my_waves) + n_local * args.beam * 448 * 4
+    # bytes the e2e step moves per rank, counted from the buffers libwlb200 copies: PCM up (wl_mel_device; the log-mel and
+    # the encoder input never leave HBM), prompts + per-stream metadata up, and per generate call the finished-hypothesis
+    # tables down (wl_generate: hyp_tok [B][16][448] + lengths / scores / counters)
+    h2d = sum(w.nbytes for w in my_waves) + n_local * (448 + 16) * 4
+    d2h = n_local * (16 * 448 * 4 + 16 * 8 + 16)
+    if args.word_timestamps:   # K14: text-token probabilities + DTW path (<= 448 + 1500 pairs) per stream
+        d2h += n_local * ((448 + 1500 + 2) * 8 + 448 * 4)
 
     # ---- roofline of the dominant kernel (cross-attention K/V streaming), measured live
     roof = dominant_kernel_roofline(eng, dims, n_local, args.beam, feats_cache)

@@ -39,6 +39,12 @@ class OracleEncoderOutput:
         return OracleEncoderOutput(self.enc.index_select(0, idx),
                                    [(k.index_select(0, idx), v.index_select(0, idx)) for k, v in self.xkv])
 
+    def join(self, views):
+        """Batch of several (single- or multi-stream) views: the oracle's handles are tensors, so they concatenate."""
+        return OracleEncoderOutput(torch.cat([v.enc for v in views], 0),
+                                   [(torch.cat([v.xkv[l][0] for v in views], 0), torch.cat([v.xkv[l][1] for v in views], 0))
+                                    for l in range(len(self.xkv))])
+
     def __array__(self, dtype=None, copy=None):
         a = self.enc.numpy()
         return a.astype(dtype) if dtype is not None else a

@@ -81,8 +81,10 @@ def _oracle_model(name="micro.en", seed=0):
                             feature_extractor=OracleFeatureExtractor(dims.n_mels))
 
 
-def test_scheduler_batches_and_survives_errors():
-    from whisperlive_b200.scheduler import BatchRequest, StreamScheduler
+def test_scheduler_survives_errors_and_isolates_them():
+    """The owner thread keeps serving after a failing call; with a plain ``transcribe_batch`` transcriber (no sessions)
+    every round is one call over whatever is in the inbox."""
+    from whisperlive_b200.scheduler import BatchRequest, RoundScheduler
 
     class Fake:
         def __init__(self):
@@ -94,7 +96,7 @@ def test_scheduler_batches_and_survives_errors():
                 raise RuntimeError("boom")
             return [([f"seg{len(a)}"], "info") for a in audios]
     fake = Fake()
-    sch = StreamScheduler(fake, max_batch_size=4, batch_window_ms=200)
+    sch = RoundScheduler(fake, max_batch_size=4, linger_ms=200)
     sch.start()
     reqs = [BatchRequest(audio=np.zeros(n, np.float32), use_vad=False) for n in (5, 6, 7)]
     for r in reqs:
@@ -106,8 +108,53 @@ def test_scheduler_batches_and_survives_errors():
     assert bad.future.wait(5) and isinstance(bad.error, RuntimeError)
     ok = BatchRequest(audio=np.zeros(2, np.float32))
     sch.submit(ok)
-    assert ok.future.wait(5) and ok.result == ["seg2"]   # worker is still alive
+    assert ok.future.wait(5) and ok.result == ["seg2"]   # the owner thread is still alive
     sch.stop()
+
+
+def test_round_scheduler_admits_mid_flight_and_answers_early():
+    """N2: a chunk submitted while others are already decoding joins THEIR rounds (it is not queued behind the batch),
+    and a short chunk is answered before a long multi-window one it shared rounds with; results equal the one-shot
+    ``transcribe_batch`` of the same audio."""
+    from whisperlive_b200 import synth
+    from whisperlive_b200.scheduler import BatchRequest, RoundScheduler
+    torch.set_num_threads(4)
+    model = _oracle_model()
+    long_wave, short_wave = synth.speech_like(65.0, seed=50), synth.speech_like(3.0, seed=51)
+
+    class Req(BatchRequest):      # no sampling rungs: the comparison below is token for token
+        def kwargs(self):
+            return dict(super().kwargs(), temperature=[0.0], log_prob_threshold=None)
+    BatchRequest = Req
+    ref = model.transcribe_batch([long_wave, short_wave], [Req(audio=long_wave, use_vad=False, language="en").kwargs()] * 2)
+
+    entered = threading.Event()
+    orig_round = type(model.open_session()).round
+
+    sch = RoundScheduler(model, max_batch_size=4)
+
+    def patched_round(self_):
+        entered.set()
+        return orig_round(self_)
+    sess_cls = type(model.open_session())
+    sess_cls.round = patched_round
+    try:
+        sch.start()
+        r_long = BatchRequest(audio=long_wave, use_vad=False, language="en")
+        sch.submit(r_long)
+        assert entered.wait(30)                      # the long stream is being decoded (3 windows ahead of it)
+        r_short = BatchRequest(audio=short_wave, use_vad=False, language="en")
+        sch.submit(r_short)
+        assert r_short.future.wait(120) and r_long.future.wait(240)
+    finally:
+        sess_cls.round = orig_round
+        sch.stop()
+    assert r_short.error is None and r_long.error is None
+    assert sch.admitted_mid_flight >= 1 and sch.max_in_flight == 2
+    assert r_short.finished_at < r_long.finished_at      # answered without waiting for the stream it shared rounds with
+    for r, (segs, _info) in zip((r_long, r_short), ref):
+        assert [s.tokens for s in r.result] == [s.tokens for s in segs]
+        assert [(s.start, s.end) for s in r.result] == [(s.start, s.end) for s in segs]
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")

@@ -176,17 +176,27 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int key0 = j * FA_BK + half * 64;
       const int nvalid = S_ENC - key0;                    // keys of this half that exist (only the last tile is ragged)
       const uint32_t s_addr = tmem_S[j & 1] + lane_off + half * 64;
+      // Only the 12th key tile is ragged (1500 = 11 x 128 + 92).  The mask test used to be evaluated for every score
+      // of every tile (ISETP + FSEL = 20 % of the kernel's instructions, source-level ncu page of round 1); now the full
+      // tiles run a path without it.
+      const bool ragged = nvalid < 64;
       // pass 1: raw row max over this thread's 64 keys
       float mx_raw = -INFINITY;
+      if (!ragged) {
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c0, v);
-        tmem_ld_wait();
-        if (nvalid >= c0 + 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
-        } else {
+        }
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (c0 + e < nvalid) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
@@ -201,29 +211,49 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // pass 2: probabilities -> smem (swizzled), row sum
       float sum = 0.f;
       uint8_t* prow = sP + half * (FA_BQ * 128) + row * 128;
+      const float neg_mx = -mx;
+      if (!ragged) {
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c0, v);
-        tmem_ld_wait();
-        const bool full = nvalid >= c0 + 32;
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {                     // 4 chunks of 8 keys = 16 bytes
-          __align__(16) __half2 h2[4];
+          for (int g = 0; g < 4; ++g) {                     // 4 chunks of 8 keys = 16 bytes
+            __align__(16) __half2 h2[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int kk = c0 + g * 8 + 2 * e;
-            float p0 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, -mx));
-            float p1 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, -mx));
-            if (!full) {
+            for (int e = 0; e < 4; ++e) {
+              const float p0 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, neg_mx));
+              const float p1 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, neg_mx));
+              sum += p0 + p1;
+              h2[e] = __floats2half2_rn(p0, p1);
+            }
+            const int chunk = (c0 >> 3) + g;                // 16-byte chunk inside the 128-byte row
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __align__(16) __half2 h2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int kk = c0 + g * 8 + 2 * e;
+              float p0 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e]), p.scale_log2, neg_mx));
+              float p1 = fa_exp2(fmaf(__uint_as_float(v[g * 8 + 2 * e + 1]), p.scale_log2, neg_mx));
               if (kk >= nvalid) p0 = 0.f;
               if (kk + 1 >= nvalid) p1 = 0.f;
+              sum += p0 + p1;
+              h2[e] = __floats2half2_rn(p0, p1);
             }
-            sum += p0 + p1;
-            h2[e] = __floats2half2_rn(p0, p1);
+            const int chunk = (c0 >> 3) + g;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
           }
-          const int chunk = (c0 >> 3) + g;                // 16-byte chunk inside the 128-byte row
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
         }
       }
       l = l * alpha + sum;

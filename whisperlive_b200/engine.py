@@ -51,6 +51,16 @@ class _SlotRef:
         self.slots = []
 
 
+class _Borrowed:
+    """Owner stand-in of a joined handle: holds references to the real owners, releases nothing."""
+
+    def __init__(self, owners, engine):
+        self.owners, self.engine, self.slots = owners, engine, []
+
+    def release(self) -> None:
+        return
+
+
 class EncoderOutput:
     """Opaque handle playing the role of the ``ctranslate2.StorageView`` returned by encode():
     a list of pool slots (encoder output + cross-attention K/V resident in HBM)."""
@@ -66,6 +76,11 @@ class EncoderOutput:
 
     def select(self, indices: Sequence[int]) -> "EncoderOutput":
         return EncoderOutput(self._owner, [self.slots[i] for i in indices], self._d)
+
+    def join(self, views: Sequence["EncoderOutput"]) -> "EncoderOutput":
+        """One batch handle over the slots of several views (of this or other encode calls).  Borrowed: the result
+        keeps its parents alive but never releases their slots itself."""
+        return EncoderOutput(_Borrowed([v._owner for v in views], self._owner.engine), [s_ for v in views for s_ in v.slots], self._d)
 
     def release(self) -> None:
         """Explicit end of life of the encoder output and ALL its views (the transcriber calls this at the end of

@@ -453,6 +453,246 @@ class _StreamJob:
         return False
 
 
+# --------------------------------------------------------------------------- rounds
+class _Entry:
+    __slots__ = ("job", "window", "state", "parent", "index", "handle", "prepared", "error")
+
+    def __init__(self, job, handle, prepared=None):
+        self.job, self.handle, self.prepared = job, handle, prepared
+        self.window, self.state, self.parent, self.index, self.error = None, "window", None, -1, None
+
+
+class _EncGroup:
+    """One ``encode`` call's output and how many of its streams are still decoding (slots go back when the last one is done)."""
+
+    def __init__(self, enc, n):
+        self.enc, self.left = enc, n
+
+    def done_one(self):
+        self.left -= 1
+        if self.left == 0:
+            release = getattr(self.enc, "release", None)
+            if release is not None:
+                release()             # encoder slots back to the pool NOW (explicit, not refcount-driven)
+            self.enc = None
+
+
+class TranscribeSession:
+    """The window / fallback state machines of many streams advanced in ROUNDS.  One round =
+      1. encode the next 30 s window of every stream that needs one (groups of at most ``engine.max_streams``, never
+         more windows than the encoder slot pool has free),
+      2. ONE ``generate`` call per distinct option set over every stream that has a window to decode -- first attempts
+         and temperature-fallback retries of different streams share the call when their options agree,
+      3. batched word alignment + window post-processing of the streams whose decode settled.
+    Streams are independent, so a stream's result does not depend on who shares its rounds; but nobody waits for a
+    whole batch: a stream added between two rounds joins the next one, a multi-window stream does not hold the others
+    in lock-step, and a finished stream's slots are refilled immediately.  (The reference's batcher assembles a batch,
+    runs it to completion -- first window only -- and re-encodes on every fallback rung: batch_inference.py:155-187,
+    :259, :334-339.)  ``B200WhisperModel.transcribe_batch`` is this with all streams added up front."""
+
+    def __init__(self, model: "B200WhisperModel"):
+        self.m = model
+        self.entries: List[_Entry] = []
+        self._next_handle = 0
+        self.rounds = 0
+
+    # -- admission -------------------------------------------------------------------------------
+    def add_job(self, job: _StreamJob, prepared: Optional[dict] = None) -> int:
+        h = self._next_handle
+        self._next_handle += 1
+        e = _Entry(job, h, prepared)
+        e.window = job.advance_window()
+        if e.window is None:
+            e.state = "done"
+        self.entries.append(e)
+        return h
+
+    def add_streams(self, audios: Sequence[np.ndarray], per_stream_kwargs: Optional[Sequence[dict]] = None,
+                    resident_ok: bool = False) -> List[int]:
+        """Admit streams (reference ``WhisperModel.transcribe`` :811-968 up to the window loop, batched): VAD clipping,
+        ONE mel call for all of them, language resolution, options.  ``resident_ok``: the features may stay in HBM
+        (valid until the next mel call on this engine, i.e. only when nothing else is admitted before these streams
+        finish -- ``transcribe_batch``); a scheduler that keeps admitting takes the host-returning extractor."""
+        m = self.m
+        n = len(audios)
+        kws = list(per_stream_kwargs) if per_stream_kwargs is not None else [{} for _ in range(n)]
+        tm = getattr(m, "last_timing", None) or {}
+        t0 = time.perf_counter()
+        prepared = [m._prepare_stream(np.asarray(a), dict(k)) for a, k in zip(audios, kws)]
+        tm["prepare"] = tm.get("prepare", 0.0) + time.perf_counter() - t0
+        handles: List[int] = []
+        live = [i for i, p in enumerate(prepared) if p is not None]
+        feats: List[Any] = []
+        if live:
+            t0 = time.perf_counter()
+            fe = m.feature_extractor
+            cap = int(getattr(m.model, "max_streams", 0) or 0)
+            chunk_length = prepared[live[0]]["kw"].get("chunk_length")
+            if resident_ok and hasattr(fe, "batch_resident") and 0 < len(live) <= cap and not self.entries:
+                # mel -> encoder without leaving HBM (the reference's two host-side calls, :862 and :1348, fused on the device)
+                feats = fe.batch_resident([prepared[i]["audio"] for i in live], chunk_length=chunk_length)
+            else:
+                feats = fe.batch([prepared[i]["audio"] for i in live], chunk_length=chunk_length)
+            tm["mel"] = tm.get("mel", 0.0) + time.perf_counter() - t0
+            for i, f in zip(live, feats):
+                prepared[i]["features"] = f
+            m._resolve_languages([prepared[i] for i in live])
+        for i in range(n):
+            p = prepared[i]
+            if p is None:      # nothing left after VAD: (None, None) like reference :860-861
+                h = self._next_handle
+                self._next_handle += 1
+                e = _Entry(None, h, None)
+                e.state = "done"
+                self.entries.append(e)
+                handles.append(h)
+                continue
+            tok = Tokenizer(m.hf_tokenizer, m.model.is_multilingual, task=p["kw"]["task"], language=p["language"])
+            p["options"] = m._make_options(tok, p["kw"])
+            job = _StreamJob(m, p["features"], tok, p["options"])
+            job.single_window = p["single_window"]
+            handles.append(self.add_job(job, p))
+        return handles
+
+    def result(self, handle: int):
+        """``(segments, info)`` of a finished stream (raises what the stream raised)."""
+        return self.result_of(next(e for e in self.entries if e.handle == handle))
+
+    def result_of(self, e: "_Entry"):
+        if e.state != "done":
+            raise RuntimeError("stream is still in flight")
+        if e.error is not None:
+            raise e.error
+        if e.job is None:
+            return (None, None)
+        m, p, segs = self.m, e.prepared, e.job.segments
+        if p is None:
+            return (segs, None)
+        if p["speech_chunks"]:
+            segs = restore_speech_timestamps(segs, p["speech_chunks"], m.feature_extractor.sampling_rate, m._vad)
+        info = TranscriptionInfo(language=p["language"], language_probability=p["language_probability"], duration=p["duration"],
+                                 duration_after_vad=p["duration_after_vad"], transcription_options=p["options"],
+                                 vad_options=p["vad_parameters"], all_language_probs=p["all_language_probs"])
+        return (segs, info)
+
+    def pending(self) -> int:
+        return sum(1 for e in self.entries if e.state != "done")
+
+    def pop_finished(self) -> List[_Entry]:
+        done = [e for e in self.entries if e.state == "done"]
+        self.entries = [e for e in self.entries if e.state != "done"]
+        return done
+
+    # -- one round ---------------------------------------------------------------------------------
+    def round(self) -> None:
+        m = self.m
+        tm = getattr(m, "last_timing", None) or {}
+        self.rounds += 1
+        cap = int(getattr(m.model, "max_streams", 0) or 0) or max(1, len(self.entries))
+        # 1. encode
+        need = [e for e in self.entries if e.state == "window"]
+        free = getattr(m.model, "free_slots", None)
+        if callable(free):
+            need = need[:max(0, free())]
+        for g0 in range(0, len(need), cap):
+            grp = need[g0:g0 + cap]
+            t0 = time.perf_counter()
+            try:
+                enc = m.encode(m._stack_windows([e.window for e in grp]))
+            except Exception as ex:
+                for e in grp:
+                    e.error, e.state = ex, "done"
+                continue
+            tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
+            parent = _EncGroup(enc, len(grp))
+            for k, e in enumerate(grp):
+                j = e.job
+                e.parent, e.index, e.window = parent, k, None
+                j.enc = enc.select([k]) if hasattr(enc, "select") else _EncoderSlice(enc, k)
+                try:
+                    if j.opt.multilingual:
+                        tok_s, _p = m.model.detect_language(j.enc)[0][0]
+                        j.tok.language = j.tok.tokenizer.token_to_id(tok_s)
+                        j.tok.language_code = tok_s[2:-2]
+                    j.build_prompt()
+                    e.state = "decode"
+                except Exception as ex:
+                    self._fail(e, ex)
+        # 2. one generate call per option set
+        groups: Dict[str, List[_Entry]] = {}
+        kwargs = {}
+        for e in [e for e in self.entries if e.state == "decode"]:
+            try:
+                kw = e.job.generate_kwargs()
+            except Exception as ex:
+                self._fail(e, ex)
+                continue
+            kwargs[e.handle] = kw
+            key = {a: v for a, v in kw.items() if a != "max_length"}
+            groups.setdefault(json.dumps(key, sort_keys=True, default=list), []).append(e)
+        settled: List[_Entry] = []
+        for _key, es in groups.items():
+            kw = dict(kwargs[es[0].handle])
+            lengths = [kwargs[e.handle]["max_length"] for e in es]
+            if len(set(lengths)) > 1:
+                kw["max_length_per_stream"] = lengths
+                kw["max_length"] = max(lengths)
+            t0 = time.perf_counter()
+            try:
+                outs = m.model.generate(_join_encoded([e.job.enc for e in es]), [e.job.prompt for e in es], **kw)
+            except Exception as ex:
+                for e in es:
+                    self._fail(e, ex)
+                continue
+            t1 = time.perf_counter()
+            for e, r in zip(es, outs):
+                if e.job.accept(r):
+                    settled.append(e)
+            tm["generate"] = tm.get("generate", 0.0) + t1 - t0
+            tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
+        # 3. alignment + window post-processing of what settled
+        t0 = time.perf_counter()
+        try:
+            m._align_entries(settled)
+        except Exception as ex:
+            for e in settled:
+                self._fail(e, ex)
+            settled = []
+        for e in settled:
+            j = e.job
+            try:
+                j.finish_window()
+                if j.single_window:
+                    j.seek = j.content_frames     # bench switch: one 30 s window per chunk (pinned work)
+                nxt = j.advance_window()
+            except Exception as ex:
+                self._fail(e, ex)
+                continue
+            j.enc = None
+            e.parent.done_one()
+            e.parent = None
+            e.window, e.state = nxt, ("window" if nxt is not None else "done")
+        tm["finish"] = tm.get("finish", 0.0) + time.perf_counter() - t0
+
+    def _fail(self, e: _Entry, ex: Exception) -> None:
+        e.error, e.state = ex, "done"
+        e.job.enc = None
+        if e.parent is not None:
+            e.parent.done_one()
+            e.parent = None
+
+
+def _join_encoded(views: List[Any]):
+    """Encoder outputs of several streams (views into possibly different ``encode`` calls) as ONE batch for generate /
+    align.  Engine handles are slot lists and join without copying; a mocked engine must hand out handles with ``join``."""
+    if len(views) == 1:
+        return views[0]
+    first = views[0]
+    if hasattr(first, "join"):
+        return first.join(views)
+    raise TypeError("this engine cannot batch encoder outputs of different encode() calls")
+
+
 # --------------------------------------------------------------------------- the model
 class B200WhisperModel:
     def __init__(self, model_size_or_path: str = "small.en", device: str = "cuda", device_index: Union[int, List[int]] = 0,
@@ -552,55 +792,12 @@ class B200WhisperModel:
     def transcribe_batch(self, audios: Sequence[np.ndarray], per_stream_kwargs: Optional[Sequence[dict]] = None):
         """Transcribe several independent streams together.  Returns ``[(segments, info)]`` in
         order; an empty (after VAD) stream yields ``(None, None)`` like reference :860-861."""
-        n = len(audios)
-        kws = list(per_stream_kwargs) if per_stream_kwargs is not None else [{} for _ in range(n)]
-        results: List[Any] = [None] * n
-        jobs: List[Tuple[int, _StreamJob, dict]] = []
-        tm = self.last_timing = {"prepare": 0.0, "mel": 0.0, "encode": 0.0, "generate": 0.0, "host_decode": 0.0, "finish": 0.0}
-        t0 = time.perf_counter()
-        prepared = [self._prepare_stream(np.asarray(a), dict(k)) for a, k in zip(audios, kws)]
-        tm["prepare"] = time.perf_counter() - t0
-        # mel for all non-empty streams in one device call
-        live = [i for i, p in enumerate(prepared) if p is not None]
-        for i in range(n):
-            if prepared[i] is None:
-                results[i] = (None, None)
-        if not live:
-            return results
-        t0 = time.perf_counter()
-        fe = self.feature_extractor
-        cap = int(getattr(self.model, "max_streams", 0) or 0)
-        if hasattr(fe, "batch_resident") and 0 < len(live) <= cap:
-            # mel -> encoder without leaving HBM (the reference's two host-side calls, :862 and :1348, fused on the device)
-            feats = fe.batch_resident([prepared[i]["audio"] for i in live], chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
-        else:
-            feats = fe.batch([prepared[i]["audio"] for i in live], chunk_length=prepared[live[0]]["kw"].get("chunk_length"))
-        tm["mel"] = time.perf_counter() - t0
-        for i, f in zip(live, feats):
-            prepared[i]["features"] = f
-        self._resolve_languages([prepared[i] for i in live])
-        for i in live:
-            p = prepared[i]
-            tok = Tokenizer(self.hf_tokenizer, self.model.is_multilingual, task=p["kw"]["task"], language=p["language"])
-            opts = self._make_options(tok, p["kw"])
-            p["options"] = opts
-            job = _StreamJob(self, p["features"], tok, opts)
-            job.single_window = p["single_window"]
-            jobs.append((i, job, p))
-        self._run_jobs([j for _, j, _ in jobs])
-        t0 = time.perf_counter()
-        for i, job, p in jobs:
-            segs = job.segments
-            if p["speech_chunks"]:
-                segs = restore_speech_timestamps(segs, p["speech_chunks"], self.feature_extractor.sampling_rate,
-                                                 self._vad)
-            info = TranscriptionInfo(language=p["language"], language_probability=p["language_probability"],
-                                     duration=p["duration"], duration_after_vad=p["duration_after_vad"],
-                                     transcription_options=p["options"], vad_options=p["vad_parameters"],
-                                     all_language_probs=p["all_language_probs"])
-            results[i] = (segs, info)
-        tm["finish"] = time.perf_counter() - t0
-        return results
+        self.last_timing = {"prepare": 0.0, "mel": 0.0, "encode": 0.0, "generate": 0.0, "host_decode": 0.0, "finish": 0.0}
+        sess = TranscribeSession(self)
+        handles = sess.add_streams(audios, per_stream_kwargs, resident_ok=True)
+        while sess.pending():
+            sess.round()
+        return [sess.result(h) for h in handles]
 
     # -- stream preparation (reference :811-861) --------------------------------------------------
     _DEFAULTS = dict(language=None, task="transcribe", log_progress=False, beam_size=5, best_of=5, patience=1,
@@ -692,93 +889,40 @@ class B200WhisperModel:
             max_new_tokens=kw["max_new_tokens"], clip_timestamps=kw["clip_timestamps"],
             hallucination_silence_threshold=kw["hallucination_silence_threshold"], hotwords=kw["hotwords"])
 
-    # -- the lockstep scheduler ------------------------------------------------------------------
+    # -- the round scheduler ---------------------------------------------------------------------
     def _run_jobs(self, jobs: List[_StreamJob]) -> None:
-        """Advance all streams window by window; every device call covers every live stream (in groups of at most
-        ``engine.max_streams``: the encoder slot pool holds 2 x max_streams windows, and a group's slots are handed
-        back explicitly before the next group / window is encoded -- never left to the garbage collector)."""
-        cap = int(getattr(self.model, "max_streams", 0) or 0) or len(jobs) or 1
-        while True:
-            windows = [(j, j.advance_window()) for j in jobs]
-            live_all = [(j, w) for j, w in windows if w is not None]
-            if not live_all:
-                return
-            for g0 in range(0, len(live_all), cap):
-                self._run_window_group(live_all[g0:g0 + cap])
+        """Run the window state machines of ``jobs`` to completion (``transcribe_batch``, ``generate_segments``)."""
+        sess = TranscribeSession(self)
+        for j in jobs:
+            sess.add_job(j)
+        while sess.pending():
+            sess.round()
+        for e in sess.entries:
+            if e.error is not None:
+                raise e.error
 
-    def _run_window_group(self, live: List[Tuple[_StreamJob, np.ndarray]]) -> None:
-        tm = getattr(self, "last_timing", None) or {}
-        t0 = time.perf_counter()
-        enc = self.encode(self._stack_windows([w for _, w in live]))
-        tm["encode"] = tm.get("encode", 0.0) + time.perf_counter() - t0
-        try:
-            for k, (j, _) in enumerate(live):
-                j.enc = enc.select([k]) if hasattr(enc, "select") else _EncoderSlice(enc, k)
-                if j.opt.multilingual:
-                    tok_s, _p = self.model.detect_language(j.enc)[0][0]
-                    j.tok.language = j.tok.tokenizer.token_to_id(tok_s)
-                    j.tok.language_code = tok_s[2:-2]
-                j.build_prompt()
-            pending = list(range(len(live)))
-            while pending:
-                # group streams whose generate() arguments are identical (temperature rung, beam, ...)
-                # (max_length may differ per stream -- ragged max_new_tokens -- and is passed per stream)
-                groups: Dict[str, List[int]] = {}
-                kwargs = {k: live[k][0].generate_kwargs() for k in pending}
-                for k in pending:
-                    key = {a: v for a, v in kwargs[k].items() if a != "max_length"}
-                    groups.setdefault(json.dumps(key, sort_keys=True, default=list), []).append(k)
-                nxt = []
-                for _key, ks in groups.items():
-                    kw = dict(kwargs[ks[0]])
-                    lengths = [kwargs[k]["max_length"] for k in ks]
-                    if len(set(lengths)) > 1:
-                        kw["max_length_per_stream"] = lengths
-                        kw["max_length"] = max(lengths)
-                    sub = enc.select(ks) if hasattr(enc, "select") else _EncoderSlice(enc, ks)
-                    t0 = time.perf_counter()
-                    outs = self.model.generate(sub, [live[k][0].prompt for k in ks], **kw)
-                    t1 = time.perf_counter()
-                    del sub
-                    for k, r in zip(ks, outs):
-                        if not live[k][0].accept(r):
-                            nxt.append(k)
-                    tm["generate"] = tm.get("generate", 0.0) + t1 - t0
-                    tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
-                pending = sorted(nxt)
-            t0 = time.perf_counter()
-            self._align_windows([j for j, _ in live], enc)
-            for j, _ in live:
-                j.finish_window()
-                if j.single_window:
-                    j.seek = j.content_frames     # bench switch: one 30 s window per chunk (pinned work)
-            tm["finish"] = tm.get("finish", 0.0) + time.perf_counter() - t0
-        finally:
-            for j, _ in live:
-                j.enc = None
-            release = getattr(enc, "release", None)
-            if release is not None:
-                release()                         # encoder slots back to the pool NOW (explicit, not refcount-driven)
-            del enc
+    def open_session(self) -> "TranscribeSession":
+        """Incremental front end for a scheduler: ``add()`` streams at any time, ``round()`` advances everything that
+        is in flight by one device round."""
+        return TranscribeSession(self)
 
-    def _align_windows(self, jobs: List[_StreamJob], enc) -> None:
+    def _align_entries(self, entries: List["_Entry"]) -> None:
         """K14 batched: ONE ``align`` call (one teacher-forced pass over all positions of all streams, DTW on the device)
-        for every stream of the window that wants word timestamps -- the reference aligns stream by stream
+        for every stream of the round that wants word timestamps -- the reference aligns stream by stream
         (:1230, :1657-1663).  Streams are grouped by sot sequence (language / task), which ``align`` takes once per call.
-        The per-stream call inside ``finish_window`` remains the fallback for engines without ``select``."""
-        if not hasattr(enc, "select"):
-            return
-        groups: Dict[Tuple[int, ...], List[Tuple[int, _StreamJob, List[int]]]] = {}
-        for k, j in enumerate(jobs):
-            if not j.opt.word_timestamps:
+        The per-stream call inside ``finish_window`` remains the fallback for engines whose handles cannot be joined."""
+        groups: Dict[Tuple[int, ...], List[Tuple[_StreamJob, List[int]]]] = {}
+        for e in entries:
+            j = e.job
+            if not j.opt.word_timestamps or not hasattr(j.enc, "join"):
                 continue
             toks = j.alignment_request()
             if toks is not None:
-                groups.setdefault(tuple(j.tok.sot_sequence), []).append((k, j, toks))
+                groups.setdefault(tuple(j.tok.sot_sequence), []).append((j, toks))
         for sot_seq, items in groups.items():
-            res = self.model.align(enc.select([k for k, _, _ in items]), list(sot_seq), [t for _, _, t in items],
-                                   [j.segment_size for _, j, _ in items], median_filter_width=7)
-            for (_, j, _), r in zip(items, res):
+            res = self.model.align(_join_encoded([j.enc for j, _ in items]), list(sot_seq), [t for _, t in items],
+                                   [j.segment_size for j, _ in items], median_filter_width=7)
+            for (j, _), r in zip(items, res):
                 j._align_result = r
 
     def _stack_windows(self, views: List[np.ndarray]) -> np.ndarray:
