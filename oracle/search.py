@@ -298,7 +298,7 @@ def search_stream(step_fn, prompt: List[int], spec: VocabSpec, opts: GenOptions,
                                  for r in range(n_alive)]).reshape(-1)
             if opts.trace:
                 tv, ti = topk_stable(total, 2 * K + 2)
-                res.trace.append({"alive": [tuple(t) for t in alive_tokens],
+                res.trace.append({"alive": [tuple(t) for t in alive_tokens], "alive_cum": [float(c) for c in alive_cum],
                                   "cand": [(int(i) // spec.vocab, int(i) % spec.vocab, float(v)) for v, i in zip(tv, ti)]})
             vals, idx = topk_stable(total, 2 * K)
             n_c = idx.shape[0]

@@ -445,7 +445,10 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
 
   // ---- encoder workspaces (EB streams per pass, AB streams per attention sub-pass)
   const int H = c->H;
-  c->EB = std::min(c->Bm, 8);
+  // streams per encoder pass: 16 x 1500 = 24000 rows fill the 148 SMs' tile waves better than 12000 (7 waves at 91 % vs
+  // 13 at 98 % for the 2560-wide projection); the workspaces are ~1 GB at large-v3, nothing next to 180 GB
+  static const int enc_batch = [] { const char* e = getenv("WLB200_ENC_BATCH"); return e ? std::max(1, atoi(e)) : 16; }();
+  c->EB = std::min(c->Bm, enc_batch);
   c->AB = std::min(c->EB, d >= 1024 ? 2 : 4);
   const size_t M = (size_t)c->EB * S_ENC;
   c->feat32 = dalloc<float>(c, (size_t)c->Bm * nm * 3000);  // all streams of a call stay resident (wl_encode_resident)
