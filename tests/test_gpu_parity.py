@@ -374,13 +374,13 @@ def test_batched_prefill_equals_token_by_token(name, beam):
     b = eng.generate(enc, prompts, prefill=False, **kw)
     for x, y, p in zip(a, b, prompts):
         assert abs(x.no_speech_prob - y.no_speech_prob) < 5e-3
-        if x.sequences_ids[0] != y.sequences_ids[0]:      # the GEMM kernels differ (tcgen05 tiles vs decode path): near-ties may flip
-            print("prefill vs stepwise differ:", x.scores, y.scores)
-            assert abs(x.scores[0] - y.scores[0]) < SCORE_TOL
-        else:
+        if x.sequences_ids[0] == y.sequences_ids[0]:
             assert abs(x.scores[0] - y.scores[0]) < 5e-3
+        else:   # different GEMM kernels feed the two paths (tcgen05 row tiles vs the decode path): a near-tie may flip,
+            print("prefill vs stepwise differ:", x.scores, y.scores)   # and BOTH must then be explained against the oracle below
     ref = orc.generate(oenc, prompts, **kw)
     _compare_generation(a, ref, f"prefill {name} beam{beam}", orc, oenc, prompts, kw, eng=eng, enc=enc)
+    _compare_generation(b, ref, f"stepwise {name} beam{beam}", orc, oenc, prompts, kw, eng=eng, enc=enc)
 
 
 class _EngineStep:

@@ -47,6 +47,30 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
     kv = __ldg(reinterpret_cast<const float2*>(qkv.bias + d + c0));
     vv = __ldg(reinterpret_cast<const float2*>(qkv.bias + 2 * d + c0));
   }
+  // Everything about the CACHED positions (< pos) predates this decode step -- the indirection table was written by the
+  // previous step's search kernel, the K/V rows by earlier steps (or, in the batched prefill, by the kernel before this
+  // one) -- so it is fetched BEFORE the dependency wait: the table, the K row of position `lane` and the first eight
+  // 16-byte V pieces of this lane.  After the wait only q / k / v of the new position are one L2 round trip away.
+  {
+    const short* src = s.src + (long)r * T_MAX;
+#pragma unroll 1
+    for (int p = lane; p < pos; p += 32) ssrc[p] = src[p];
+  }
+  __syncwarp();
+  uint4 kpre[8];
+  if (lane < pos) {
+    const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)ssrc[lane] * row_stride + ((long)h * T_MAX + lane) * 64);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kpre[c] = kp[c];
+  }
+  const int c8 = lane & 7, pg = lane >> 3;
+  const long hoff = (long)h * T_MAX * 64 + c8 * 8;
+  uint4 vpre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = pg + 4 * i;
+    vpre[i] = p < pos ? *reinterpret_cast<const uint4*>(vc + (long)ssrc[p] * row_stride + hoff + (long)p * 64) : make_uint4(0u, 0u, 0u, 0u);
+  }
   tl_stamp(TL_SELF, 0);
   pdl_wait();
   tl_stamp(TL_SELF, 1);
@@ -78,23 +102,20 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
     *reinterpret_cast<__half2*>(vc + o) = __floats2half2_rn(vv.x, vv.y);
   }
   const float dot_new = warp_sum(qv.x * kv.x + qv.y * kv.y);   // the new position uses the unrounded k (as before)
-  // beam indirection table of this row -> shared memory first: the K and V sweeps below then issue all their loads
-  // without a dependent global load in front of each (one L2 round trip per sweep instead of two per position)
-  {
-    const short* src = s.src + (long)r * T_MAX;
-#pragma unroll 1
-    for (int p = lane; p < pos; p += 32) ssrc[p] = src[p];
-  }
-  __syncwarp();
   float lmax = -INFINITY;
 #pragma unroll 1
   for (int p = lane; p < n; p += 32) {
     float acc = dot_new;
     if (p != pos) {
-      const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)ssrc[p] * row_stride + ((long)h * T_MAX + p) * 64);
       uint4 u[8];
+      if (p == lane) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) u[c] = kp[c];
+        for (int c = 0; c < 8; ++c) u[c] = kpre[c];
+      } else {
+        const uint4* kp = reinterpret_cast<const uint4*>(kc + (long)ssrc[p] * row_stride + ((long)h * T_MAX + p) * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) u[c] = kp[c];
+      }
       acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -123,13 +144,23 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   // weighted V sum: lane = (position group pg = lane / 8, 16-byte dim chunk c8 = lane % 8).  The 4 groups stride over
   // the cached positions with independent 16-byte loads (8 in flight per lane), then fold with two shuffles; round 1
   // walked the positions one by one with a dependent (index -> V row) load pair each: ~0.25 us per cached position.
-  const int c8 = lane & 7, pg = lane >> 3;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const long hoff = (long)h * T_MAX * 64 + c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {          // positions pg + 4 i < 32: prefetched before the wait
+    const int p = pg + 4 * i;
+    const float w = p < pos ? sc[p] : 0.f;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&vpre[i]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
+    }
+  }
 #pragma unroll 4
-  for (int p = pg; p < pos; p += 4) {
+  for (int p = pg + 32; p < pos; p += 4) {
     const float w = sc[p];
     const uint4 u = *reinterpret_cast<const uint4*>(vc + (long)ssrc[p] * row_stride + hoff + (long)p * 64);
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);

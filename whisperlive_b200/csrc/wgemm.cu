@@ -40,8 +40,6 @@ struct WgemmParams {
   __half* out_f16;     // mode 2: [R][n_out] gelu(acc + bias)
   long part_stride;    // mode 3: elements between K ranges
   int n_out, K, R, nf, kr, ksplit, mode;
-  const void* pf_ptr;  // weights of the NEXT linear layer: every CTA asks L2 for its share (no data dependency) ...
-  long pf_bytes;       // ... so that when that layer's CTAs become resident their slices are L2 hits, not an HBM stream
 };
 
 __device__ __forceinline__ void mma_16816_f32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -79,22 +77,6 @@ __global__ void __launch_bounds__(WG_WARPS * 32) wgemm_kernel(const WgemmParams 
     mbar_expect_tx(bar, (uint32_t)(nf * kr * 2));
 #pragma unroll 1
     for (int f = 0; f < nf; ++f) bulk_load_1d(sW + f * pitch, p.W + (long)(f0 + f) * p.K + k0, (uint32_t)(kr * 2), bar);
-    if (p.pf_bytes > 0) {
-      // HBM keeps streaming one layer ahead of the dependency chain: the whole layer's weights (46 MB for large-v3) fit
-      // in the 126 MB L2 at the batch sizes this kernel serves
-      const long share = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15L;
-      const long lo = (long)blockIdx.x * share;
-      long left = min(share, p.pf_bytes - lo);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.pf_ptr) + lo;
-#pragma unroll 1
-      while (left > 0) {
-        const uint32_t n = (uint32_t)min(left, 65536L) & ~15u;
-        if (n == 0) break;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n) : "memory");
-        src += n;
-        left -= n;
-      }
-    }
   }
   // epilogue assignment without divisions: thread (er = tid / 16, fl = tid % 16) owns rows er (+16 with two m-tiles)
   // and features fl, fl + 16, fl + 32 (< nf) of the CTA's tile.  Their bias (a weight) is fetched before the dependency
@@ -208,8 +190,9 @@ void wgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, 
   WgemmParams p;
   p.W = W; p.X = X; p.bias = bias; p.out_f32 = out_f32; p.out_f16 = out_f16; p.part_stride = part_stride;
   p.n_out = n_out; p.K = K; p.R = R; p.ksplit = ksplit; p.mode = mode;
-  static const bool pf_env = [] { const char* e = getenv("WLB200_WPREFETCH"); return e ? atoi(e) != 0 : true; }();
-  p.pf_ptr = prefetch_ptr; p.pf_bytes = (pf_env && prefetch_ptr) ? prefetch_bytes : 0;
+  // (prefetch_ptr / prefetch_bytes: an L2 prefetch of the next layer's weights from here was measured -- 65.0 vs 64.4 ms
+  // per 42 tokens at 4 streams, no gain: the slices are already requested 3 us ahead of the dependency -- and removed)
+  (void)prefetch_ptr; (void)prefetch_bytes;
   // K range per CTA: equal ranges, multiples of 32
   p.kr = cdiv(cdiv(K, ksplit), 32) * 32;
   // features per CTA: the smallest multiple of 8 (<= 40) for which the grid fits one wave of one CTA per SM; the weight
