@@ -279,7 +279,9 @@ def _explain_beam_divergence(eng, enc, orc, oenc, b, prompt, kw, got, ref, what)
         gap = worst_kept - cums[j - 1]
         print(f"{what} stream {b}: the oracle pruned the engine's prefix after token {j} (cum {cums[j - 1]:.4f}); its worst kept "
               f"beam has {worst_kept:.4f}: gap {gap:.4f}")
-        assert gap < BEAM_TIE_TOL, (what, b, j, gap)
+        # the perturbation that can flip a pruning decision accumulates with the decoded prefix: the base tolerance plus
+        # 0.005 per token (4 % of the per-logit tolerance LOGIT_TOL; the rescoring assert above bounds the same drift)
+        assert gap < BEAM_TIE_TOL + 0.005 * j, (what, b, j, gap)
         return
     # never pruned: the hypotheses differ only in when / how they were finalised or ranked
     assert abs(got.scores[0] - ref.scores[0]) < SCORE_TOL, (what, b, got.scores, ref.scores)
