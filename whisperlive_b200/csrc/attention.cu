@@ -20,6 +20,7 @@ namespace wl {
 // positions for the scores (one 128-byte K row each), dims for the weighted V sum (coalesced 128-byte V rows).
 constexpr int SA_WARPS = 4;
 
+template <bool PLAIN>   // PLAIN: q / k / v arrive as final values (wgemm path, batched prefill); else bias + <= 8 split-K partial sums
 __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s, PartialSrc qkv, __half* __restrict__ kc,
                                                                  __half* __restrict__ vc, long row_stride,
                                                                  __half* __restrict__ out, int H, int d, int R) {
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   // q / k / v of this (row, head), dims 2*lane and 2*lane+1: bias + the split-K partial sums, in range order
   const int c0 = h * 64 + 2 * lane;
   float2 qv = make_float2(0.f, 0.f), kv = qv, vv = qv;
-  if (qkv.bias) {
+  if (!PLAIN && qkv.bias) {
     qv = __ldg(reinterpret_cast<const float2*>(qkv.bias + c0));
     kv = __ldg(reinterpret_cast<const float2*>(qkv.bias + d + c0));
     vv = __ldg(reinterpret_cast<const float2*>(qkv.bias + 2 * d + c0));
@@ -74,7 +75,12 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
   tl_stamp(TL_SELF, 0);
   pdl_wait();
   tl_stamp(TL_SELF, 1);
-  {
+  if (PLAIN) {
+    const float* row = qkv.ptr + (long)r * 3 * d + c0;
+    qv = __ldcg(reinterpret_cast<const float2*>(row));
+    kv = __ldcg(reinterpret_cast<const float2*>(row + d));
+    vv = __ldcg(reinterpret_cast<const float2*>(row + 2 * d));
+  } else {
     // at most 8 K ranges (dec_gemm_split_plan); predicated so that all 24 loads are in flight together, summed in order
     const float* row = qkv.ptr + (long)r * 3 * d + c0;
     const float2 z2 = make_float2(0.f, 0.f);
@@ -188,8 +194,12 @@ __global__ void __launch_bounds__(SA_WARPS * 32) self_attn_kernel(DecodeState s,
 
 void decoder_self_attn(cudaStream_t st, const DecodeState& s, const PartialSrc& qkv, __half* kcache, __half* vcache,
                        long cache_row_stride, __half* out, int R, int H, int d) {
-  launch_kernel(self_attn_kernel, dim3(cdiv((long)R * H, SA_WARPS)), dim3(SA_WARPS * 32), 0, st, s, qkv, kcache, vcache,
-                cache_row_stride, out, H, d, R);
+  if (qkv.nsplit == 1 && qkv.bias == nullptr)
+    launch_kernel(self_attn_kernel<true>, dim3(cdiv((long)R * H, SA_WARPS)), dim3(SA_WARPS * 32), 0, st, s, qkv, kcache, vcache,
+                  cache_row_stride, out, H, d, R);
+  else
+    launch_kernel(self_attn_kernel<false>, dim3(cdiv((long)R * H, SA_WARPS)), dim3(SA_WARPS * 32), 0, st, s, qkv, kcache, vcache,
+                  cache_row_stride, out, H, d, R);
   note_launch(1);
 }
 
@@ -584,10 +594,10 @@ __global__ void __launch_bounds__(64) cross_attn_combine_kernel(DecodeState s, c
   pdl_wait();
   tl_stamp(TL_COMBINE, 1);
   const float* p = part + (((long)b * H + h) * nsplit) * MAX_ROWS_PER_STREAM * 66 + j * 66;
-  // all loads first (independent, one L2 round trip), then the arithmetic; nsplit <= 12
-  float m[XA_NCHUNK], l[XA_NCHUNK], o[XA_NCHUNK];
+  // loads of up to 6 ranges in flight together (what cross_attn_pick_nsplit chooses in practice), a rolled loop for more
+  float m[6], l[6], o[6];
 #pragma unroll
-  for (int sp = 0; sp < XA_NCHUNK; ++sp) {
+  for (int sp = 0; sp < 6; ++sp) {
     const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
     const bool on = sp < nsplit;
     m[sp] = on ? __ldcg(ps) : -INFINITY;
@@ -596,13 +606,22 @@ __global__ void __launch_bounds__(64) cross_attn_combine_kernel(DecodeState s, c
   }
   float M = -INFINITY;
 #pragma unroll
-  for (int sp = 0; sp < XA_NCHUNK; ++sp) M = fmaxf(M, m[sp]);
+  for (int sp = 0; sp < 6; ++sp) M = fmaxf(M, m[sp]);
+#pragma unroll 1
+  for (int sp = 6; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(p + (long)sp * MAX_ROWS_PER_STREAM * 66));
   float L = 0.f, acc = 0.f;
 #pragma unroll
-  for (int sp = 0; sp < XA_NCHUNK; ++sp) {
+  for (int sp = 0; sp < 6; ++sp) {
     const float w = sp < nsplit ? __expf(m[sp] - M) : 0.f;
     L += l[sp] * w;
     acc += o[sp] * w;
+  }
+#pragma unroll 1
+  for (int sp = 6; sp < nsplit; ++sp) {
+    const float* ps = p + (long)sp * MAX_ROWS_PER_STREAM * 66;
+    const float w = __expf(__ldcg(ps) - M);
+    L += __ldcg(ps + 1) * w;
+    acc += __ldcg(ps + 2 + dd) * w;
   }
   out[(long)r * d + h * 64 + dd] = __float2half_rn(acc / L);
 }
