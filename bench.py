@@ -398,9 +398,14 @@ def dominant_kernel_roofline(eng, dims, n_streams, beam, feats_cache):
     alg = n_streams * 2 * 1500 * d * 2          # bytes one launch has to read: K and V of every stream, fp16
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel at this configuration
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["cross_attn_kernel"]
-        if int(t.get("streams", -1)) == n_streams and t.get("model") == dims.name:
-            traffic = float(t["dram_bytes_per_launch"])
+        for fn in ("traffic_r2.json", "traffic_r1.json"):      # newest committed ncu --set full capture of this kernel
+            path = os.path.join(ROOT, "profiles", fn)
+            if not os.path.exists(path):
+                continue
+            t = json.load(open(path)).get("cross_attn_kernel", {})
+            if int(t.get("streams", -1)) == n_streams and t.get("model") == dims.name:
+                traffic = float(t["dram_bytes_per_launch"])
+                break
     except Exception:
         pass
     if avg_ms <= 0:
