@@ -116,7 +116,8 @@ int wl_test_gemm(wl_ctx* ctx, const uint16_t* a_f16, const uint16_t* b_f16, cons
                  int32_t K, int32_t batch, int32_t transposed_store, int32_t gelu, int32_t use_simt);
 /* test hook of the small-batch decode GEMM (csrc/wgemm.cu, R <= 32): out[R][n_out] = X[R][K] W[n_out][K]^T with the fused
  * epilogue `mode` -- 0: + bias; 1: out += acc + bias (residual in place); 2: gelu(acc + bias) through fp16;
- * 3: split-K partial sums (K > 1280), summed by the hook */
+ * 3: split-K partial sums (K > 1280), summed by the hook; mode | 8 (8, 9, 10): the cluster split-K GEMM (cgemm, any R)
+ * with epilogue 0, 1, 2 */
 int wl_test_wgemm(wl_ctx* ctx, const uint16_t* w_f16, const uint16_t* x_f16, const float* bias, float* out, int32_t R,
                   int32_t n_out, int32_t K, int32_t mode);
 /* device-resident timing of the GEMM kernel: C = A(MxK) * B(NxK)^T, `iters` launches between CUDA events;

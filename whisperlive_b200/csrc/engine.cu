@@ -211,6 +211,7 @@ extern "C" int wl_init(const wl_config* cfg, wl_ctx** out) {
     gemm_prime();
     dec_gemm_prime();
     wgemm_prime();
+    cgemm_prime();
     attention_prime();
     search_prime();
     flash_attn_prime();
@@ -254,7 +255,7 @@ extern "C" void wl_destroy(wl_ctx* c) {
 
 extern "C" const char* wl_last_error(wl_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
 extern "C" int64_t wl_kernel_launches(wl_ctx* c) {
-  return c ? gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
+  return c ? gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count() - c->capture_counted + c->graph_launched : 0;
 }
 extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) {
   if (!c) return -1.f;
@@ -890,29 +891,36 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   // (one m16 tile only: with two, every CTA re-reads 82 KB of X from L2 and the launch costs 8 us -- measured; rows
   // 17..32 take the tcgen05 path below until the K split moves into a cluster)
   static const int wg_max_rows = [] { const char* e = getenv("WLB200_WGEMM_ROWS"); return e ? atoi(e) : 16; }();
-  const bool small = wg_env && !simt_env && !fuse && R <= wg_max_rows && wgemm_supported(R, d) && wgemm_supported(R, ff);
+  const bool use_wg = wg_env && R <= wg_max_rows && wgemm_supported(R, d) && wgemm_supported(R, ff);
+  // Above that: cgemm, the tcgen05 pipeline with the K split inside a cluster (dec_gemm.cu) -- same fused epilogues, so
+  // the layer is the same 12 launches at every batch size.  WLB200_CGEMM=0 falls back to split-K partials (13 launches).
+  static const bool cg_env = [] { const char* e = getenv("WLB200_CGEMM"); return e ? atoi(e) != 0 : true; }();
+  const bool small = !simt_env && !fuse && (use_wg || cg_env);
   auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
+  // mode 0: out_f32 = X W^T + bias; 1: out_f32 += X W^T + bias; 2: out_f16 = gelu(X W^T + bias)
+  auto lin = [&](const __half* W, int n_out, int K, const __half* X, const float* bias, int mode, float* of32, __half* of16) {
+    if (use_wg) wgemm(st, W, n_out, K, X, R, bias, mode, of32, of16, 0);
+    else cgemm(st, W, n_out, K, X, R, bias, mode, of32, of16);
+  };
   for (int l = 0; small && l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    const long dd2 = (long)d * d * 2;   // bytes of a d x d fp16 matrix; every launch prefetches the NEXT layer's weights into L2
-    const __half* next_qkv = l + 1 < c->Ld ? c->dec[l + 1].w_qkv : nullptr;
     layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
-    wgemm(st, L.w_qkv, 3 * d, d, c->dxn, R, L.b_qkv, 0, c->part1, nullptr, 0, L.w_o, dd2);
+    lin(L.w_qkv, 3 * d, d, c->dxn, L.b_qkv, 0, c->part1, nullptr);
     decoder_self_attn(st, s, plain(c->part1), c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
-    wgemm(st, L.w_o, d, d, c->datt, R, L.b_o, 1, c->dx, nullptr, 0, L.w_qc, dd2);
+    lin(L.w_o, d, d, c->datt, L.b_o, 1, c->dx, nullptr);
     layernorm_update_rows(st, c->dx, PartialSrc(), L.ln2_g, L.ln2_b, c->dxn, R, d);
-    wgemm(st, L.w_qc, d, d, c->dxn, R, L.b_qc, 0, c->part1, nullptr, 0, L.w_oc, dd2);
+    lin(L.w_qc, d, d, c->dxn, L.b_qc, 0, c->part1, nullptr);
     cross(l, plain(c->part1));
-    wgemm(st, L.w_oc, d, d, c->datt, R, L.b_oc, 1, c->dx, nullptr, 0, L.w_fc1, 4 * dd2);
+    lin(L.w_oc, d, d, c->datt, L.b_oc, 1, c->dx, nullptr);
     layernorm_update_rows(st, c->dx, PartialSrc(), L.ln3_g, L.ln3_b, c->dxn, R, d);
-    wgemm(st, L.w_fc1, ff, d, c->dxn, R, L.b_fc1, 2, nullptr, c->dh, 0, L.w_fc2, 4 * dd2);
-    const int ks2 = wgemm_ksplit(ff);
+    lin(L.w_fc1, ff, d, c->dxn, L.b_fc1, 2, nullptr, c->dh);
+    const int ks2 = use_wg ? wgemm_ksplit(ff) : 1;
     if (ks2 == 1) {
-      wgemm(st, L.w_fc2, d, ff, c->dh, R, L.b_fc2, 1, c->dx, nullptr, 0, next_qkv, 3 * dd2);
+      lin(L.w_fc2, d, ff, c->dh, L.b_fc2, 1, c->dx, nullptr);
       pending = PartialSrc();
-    } else {   // K = 4d is split over CTAs: the next LayerNorm folds the ranges (+ bias) into x
-      wgemm(st, L.w_fc2, d, ff, c->dh, R, nullptr, 3, c->part2, nullptr, (long)c->Rm * d, next_qkv, 3 * dd2);
+    } else {   // wgemm with K = 4d split over CTAs: the next LayerNorm folds the ranges (+ bias) into x
+      wgemm(st, L.w_fc2, d, ff, c->dh, R, nullptr, 3, c->part2, nullptr, (long)c->Rm * d);
       pending.ptr = c->part2; pending.nsplit = ks2; pending.stride = (long)c->Rm * d; pending.bias = L.b_fc2;
     }
   }
@@ -1271,7 +1279,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
              so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
     GraphEntry& ge = c->graphs[key];
     if (!ge.exec) {
-      const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count();
+      const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count();
       cudaGraph_t g = nullptr, cap = nullptr;
       if (loop_graph) {
         WL_CUDA(cudaGraphCreate(&g, 0));
@@ -1304,7 +1312,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
         }
         WL_CUDA(cudaStreamEndCapture(st, &g));
       }
-      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + other_launch_count() - before;
+      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count() - before;
       c->capture_counted += ge.kernels;
       WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
       cudaGraphDestroy(g);
@@ -1593,12 +1601,14 @@ extern "C" int wl_test_gemm(wl_ctx* c, const uint16_t* a_f16, const uint16_t* b_
 extern "C" int wl_test_wgemm(wl_ctx* c, const uint16_t* w_f16, const uint16_t* x_f16, const float* bias, float* out, int32_t R,
                              int32_t n_out, int32_t K, int32_t mode) {
   API_BEGIN(c)
-  WL_CHECK(w_f16 && x_f16 && out && mode >= 0 && mode <= 3, WL_ERR_ARG, "wl_test_wgemm: bad arguments");
-  WL_CHECK(wgemm_supported(R, K), WL_ERR_ARG, "wl_test_wgemm: unsupported shape R=%d K=%d", R, K);
+  const bool clustered = (mode & 8) != 0;   // modes 8, 9, 10: the cluster split-K GEMM (cgemm) with epilogue 0, 1, 2
+  mode &= 7;
+  WL_CHECK(w_f16 && x_f16 && out && mode >= 0 && mode <= (clustered ? 2 : 3), WL_ERR_ARG, "wl_test_wgemm: bad arguments");
+  WL_CHECK(clustered || wgemm_supported(R, K), WL_ERR_ARG, "wl_test_wgemm: unsupported shape R=%d K=%d", R, K);
   __half *dw = nullptr, *dx = nullptr, *dh = nullptr;
   float *db = nullptr, *dout = nullptr;
   const size_t nw = (size_t)n_out * K, nx = (size_t)R * K, no = (size_t)R * n_out;
-  const int ks = wgemm_ksplit(K);
+  const int ks = clustered ? 1 : wgemm_ksplit(K);
   WL_CUDA(cudaMalloc((void**)&dw, nw * 2));
   WL_CUDA(cudaMalloc((void**)&dx, nx * 2));
   WL_CUDA(cudaMalloc((void**)&dh, no * 2));
@@ -1611,7 +1621,8 @@ extern "C" int wl_test_wgemm(wl_ctx* c, const uint16_t* w_f16, const uint16_t* x
     if (mode == 1) WL_CUDA(cudaMemcpy(dout, out, no * 4, cudaMemcpyHostToDevice));
     if (bias) WL_CUDA(cudaMemcpy(db, bias, (size_t)n_out * 4, cudaMemcpyHostToDevice));
     WL_CUDA(cudaDeviceSynchronize());
-    wgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh, (long)no, dw, (long)nw * 2);
+    if (clustered) cgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh);
+    else wgemm(c->st, dw, n_out, K, dx, R, bias ? db : nullptr, mode, dout, dh, (long)no);
     WL_CUDA(cudaStreamSynchronize(c->st));
     if (mode == 2) {
       std::vector<__half> h(no);

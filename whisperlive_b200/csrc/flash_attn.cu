@@ -17,7 +17,7 @@ constexpr int FA_K_BYTES = FA_BK * 128;              // 128 keys x 64 halves
 constexpr int FA_V_BYTES = 2 * 64 * 128;             // two k-blocks of [64 dd][64 keys]
 constexpr int FA_P_BYTES = 2 * FA_BQ * 128;          // two k-blocks of [128 rows][64 keys]
 constexpr int FA_STAGE_BYTES = FA_K_BYTES + FA_V_BYTES;
-constexpr int FA_SMEM = 1024 + FA_Q_BYTES + FA_STAGES * FA_STAGE_BYTES + FA_P_BYTES + 256;
+constexpr int FA_SMEM = 1024 + FA_Q_BYTES + FA_STAGES * FA_STAGE_BYTES + 2 * FA_P_BYTES + 256;   // P is double buffered
 constexpr int FA_NT = (S_ENC + FA_BK - 1) / FA_BK;   // 12 key tiles
 
 struct FaParams {
@@ -47,16 +47,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = base;
   uint8_t* sKV = sQ + FA_Q_BYTES;
   uint8_t* sP = sKV + FA_STAGES * FA_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                 // [FA_STAGES]
   uint64_t* kv_empty = kv_full + FA_STAGES;     // [FA_STAGES]
   uint64_t* s_full = kv_empty + FA_STAGES;      // [2]
   uint64_t* s_empty = s_full + 2;               // [2]
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* o_full = p_full + 1;
-  uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* p_full = s_empty + 2;               // [2]
+  uint64_t* o_full = p_full + 2;                // [2]
+  uint64_t* o_empty = o_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
   __shared__ float smax[2][2][FA_BQ];   // [tile parity][column half][row]: per-tile row-max exchange
 
   const int warp = threadIdx.x >> 5;
@@ -71,9 +71,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(q_full, 1);
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
-    mbar_init(p_full, 8);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 8); mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -85,7 +83,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_S[2] = {tmem, tmem + 128};
-  const uint32_t tmem_O = tmem + 256;
+  // P (shared memory) and O_blk (TMEM) are double buffered like S: the softmax warps fold O_blk of tile j-1 into their
+  // registers only AFTER they have written P of tile j, so they never sit out the P V MMA of the tile they just fed
+  // (single-buffered, every tile paid that round trip between its two passes: tensor pipe 19 % busy, round-1 profile).
+  const uint32_t tmem_O[2] = {tmem + 256, tmem + 320};
 
   if (warp == 0) {
     if (elect_one()) {
@@ -113,20 +114,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       constexpr uint32_t idesc_s = umma_idesc_f16(FA_BQ, FA_BK);
       constexpr uint32_t idesc_o = umma_idesc_f16(FA_BQ, 64);
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
       auto issue_pv = [&](int i) {
-        const int st = i % FA_STAGES;
-        mbar_wait(p_full, i & 1);                 // P_i written by the softmax warps
-        mbar_wait(o_empty, (i & 1) ^ 1);          // O_blk of tile i-1 consumed
+        const int st = i % FA_STAGES, pb = i & 1;
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + pb * FA_P_BYTES));
+        mbar_wait(&p_full[pb], par);              // P_i written by the softmax warps
+        mbar_wait(&o_empty[pb], par ^ 1);         // O_blk of tile i-2 (same buffer) consumed
         tc_fence_after();
         const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * FA_STAGE_BYTES + FA_K_BYTES));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t a = pdesc + (uint64_t)((kk >> 2) * (FA_BQ * 128 >> 4) + (kk & 3) * 2);
           const uint64_t bd = vdesc + (uint64_t)((kk >> 2) * (64 * 128 >> 4) + (kk & 3) * 2);
-          umma_f16(tmem_O, a, bd, idesc_o, kk > 0 ? 1u : 0u);
+          umma_f16(tmem_O[pb], a, bd, idesc_o, kk > 0 ? 1u : 0u);
         }
-        umma_commit(o_full);
+        umma_commit(&o_full[pb]);
         umma_commit(&kv_empty[st]);
       };
       mbar_wait(q_full, 0);
@@ -156,18 +158,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int e = 0; e < 32; ++e) o[e] = 0.f;
     auto accumulate_o = [&](int i, float m_i) {
       // O += PV_i, where PV_i was formed with probabilities relative to m_i
-      mbar_wait(o_full, i & 1);
+      mbar_wait(&o_full[i & 1], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const float resc = (m_ref == -INFINITY) ? 0.f : fa_exp2(m_ref - m_i);
       uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
+      tmem_ld_32x32(tmem_O[i & 1] + lane_off + half * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], resc, __uint_as_float(v[e]));
       m_ref = m_i;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      if (lane == 0) mbar_arrive(&o_empty[i & 1]);
     };
     float m_prev_tile = -INFINITY;
     for (int j = 0; j < FA_NT; ++j) {
@@ -206,11 +208,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       softmax_sync();                                     // both halves of every row have published their max
       const float mx = fmaxf(m, fmaxf(mx_raw, smax[j & 1][half ^ 1][row]) * p.scale_log2);
       const float alpha = (m == -INFINITY) ? 0.f : fa_exp2(m - mx);
-      // the P buffer (and O_blk) of the previous tile must have been consumed by its PV MMA
-      if (j >= 1) accumulate_o(j - 1, m_prev_tile);
-      // pass 2: probabilities -> smem (swizzled), row sum
+      // pass 2: probabilities -> smem (swizzled), row sum.  P[j & 1] is free: O_blk of tile j-2, i.e. the completion of
+      // the MMA that read it, was folded in at the end of iteration j-1.
       float sum = 0.f;
-      uint8_t* prow = sP + half * (FA_BQ * 128) + row * 128;
+      uint8_t* prow = sP + (j & 1) * FA_P_BYTES + half * (FA_BQ * 128) + row * 128;
       const float neg_mx = -mx;
       if (!ragged) {
 #pragma unroll
@@ -258,14 +259,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       l = l * alpha + sum;
       m = mx;
-      m_prev_tile = mx;
       tc_fence_before();
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&s_empty[j & 1]);
-        mbar_arrive(p_full);
+        mbar_arrive(&p_full[j & 1]);
       }
+      if (j >= 1) accumulate_o(j - 1, m_prev_tile);   // its P V MMA was fed one whole tile ago
+      m_prev_tile = mx;
     }
     accumulate_o(FA_NT - 1, m_prev_tile);
     // total row sum = sum of the two halves (same running max in both)

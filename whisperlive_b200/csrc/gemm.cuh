@@ -77,6 +77,13 @@ int dec_gemm_split_plan(int n_out, int R, int K, int max_split = 8);
 long dec_gemm_launch_count();
 void dec_gemm_prime();
 void dec_gemm_tl_bind(unsigned long long* p);
+// The same pipeline with the K split inside a thread-block cluster and the reduction through distributed shared memory:
+// final values with the epilogue fused (mode 0: + bias; 1: out_f32 += acc + bias; 2: out_f16 = gelu(acc + bias)).
+void cgemm(cudaStream_t st, const __half* W, int n_out, int K, const __half* X, int R, const float* bias, int mode, float* out_f32,
+           __half* out_f16);
+int cgemm_split_plan(int n_out, int R, int K);
+long cgemm_launch_count();
+void cgemm_prime();
 
 // Small-batch decode GEMM with fused epilogue (wgemm.cu, R <= 32 rows, mma.sync + bulk-copied weight slices).
 // mode 0: out_f32 = acc + bias; 1: out_f32 += acc + bias (in place); 2: out_f16 = gelu(acc + bias);

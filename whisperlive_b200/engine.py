@@ -457,7 +457,8 @@ class B200Whisper:
 
     def test_wgemm(self, w: np.ndarray, x: np.ndarray, bias: Optional[np.ndarray] = None, mode: int = 0,
                    resid: Optional[np.ndarray] = None) -> np.ndarray:
-        """Y[R, n_out] = X[R, K] W[n_out, K]^T through the small-batch decode GEMM (wl_test_wgemm)."""
+        """Y[R, n_out] = X[R, K] W[n_out, K]^T through the small-batch decode GEMM (wl_test_wgemm); ``mode | 8`` runs the
+        cluster split-K GEMM (any row count) with epilogue ``mode``."""
         w16 = np.ascontiguousarray(w, dtype=np.float16)
         x16 = np.ascontiguousarray(x, dtype=np.float16)
         n_out, K = w16.shape
