@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WL_ABI_VERSION 2
+#define WL_ABI_VERSION 3
 
 typedef struct wl_ctx wl_ctx;
 
@@ -97,6 +97,28 @@ int wl_generate(wl_ctx* ctx, const int32_t* slots, int32_t B, const int32_t* pro
                 const wl_gen_opts* opts, int32_t* out_ids, int32_t* out_len, float* out_score, float* out_no_speech,
                 int32_t* out_steps);
 
+/* N2. Decode session: step-level continuous batching -- replaces the run-to-completion batches of the reference's
+ * BatchInferenceWorker._process_multi (whisper_live/batch_inference.py:155-187; its gaps :259, :334-339).
+ *   wl_session_open    fixes the search options (wl_generate's, sampling excluded) and the number of stream indices
+ *                      (<= max_streams); every index starts idle.  Re-opening is allowed once nothing is decoding.
+ *   wl_session_admit   puts n streams into idle indices: prompts prefilled in one batched pass (K8), search state
+ *                      initialised; the streams already decoding are untouched.  max_length[n] like wl_generate's.
+ *   wl_session_run     runs the device-side token loop over every admitted stream for at most max_steps steps; with
+ *                      break_on_finish it also returns as soon as some stream has finished.  done_out[capacity]: 1 for
+ *                      indices whose stream is finished and not yet collected.  steps_ran: token steps executed.
+ *   wl_session_collect hypotheses of one finished index (outputs like one stream of wl_generate); the index goes idle.
+ *   wl_session_close   drops whatever is still in flight.
+ * The session has its own decode state and self-attention cache: wl_generate / wl_align / wl_detect_language /
+ * wl_encode may be called between two wl_session_run calls (temperature-fallback retries, word alignment of a finished
+ * window, the encoder pass of a stream about to be admitted). */
+int wl_session_open(wl_ctx* ctx, const wl_gen_opts* opts, int32_t capacity);
+int wl_session_admit(wl_ctx* ctx, int32_t n, const int32_t* index, const int32_t* slots, const int32_t* prompts,
+                     const int32_t* prompt_off, const int32_t* max_length);
+int wl_session_run(wl_ctx* ctx, int32_t max_steps, int32_t break_on_finish, int32_t* done_out, int32_t* steps_ran);
+int wl_session_collect(wl_ctx* ctx, int32_t index, int32_t* out_ids, int32_t* out_len, float* out_score, float* out_no_speech,
+                       int32_t* out_steps);
+int wl_session_close(wl_ctx* ctx);
+
 /* K13. probs [B, n_lang] softmax over the language tokens after feeding <|startoftranscript|>. */
 int wl_detect_language(wl_ctx* ctx, const int32_t* slots, int32_t B, float* probs);
 
@@ -127,7 +149,8 @@ int wl_bench_gemm(wl_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t batch, i
 /* launches of library kernels since wl_init (gpu_launches accounting in bench.py) */
 int64_t wl_kernel_launches(wl_ctx* ctx);
 /* time (ms, CUDA events on the library stream) of the last wl_mel / wl_encode / wl_generate device work;
- * which = 3: average ms per cross-attention kernel launch since wl_profile_cross_attn(ctx, 1), 4: launches timed */
+ * which = 3: average ms per cross-attention kernel launch since wl_profile_cross_attn(ctx, 1), 4: launches timed;
+ * 2 also holds the last wl_session_run, 5 the last wl_session_admit */
 float wl_last_device_ms(wl_ctx* ctx, int32_t which /*0 mel, 1 encode, 2 generate, 3/4 cross-attention profile*/);
 /* enable = 1: wl_generate calls made WITHOUT a CUDA graph bracket every cross-attention launch (K11, the dominant
  * decode kernel) with CUDA events on the library stream -- bench.py's live roofline measurement.  Resets the sums. */

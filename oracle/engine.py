@@ -145,6 +145,10 @@ class OracleWhisper:
             out.append(g)
         return out
 
+    # -- whisperlive_b200.engine.B200Whisper.open_decode_session (CPU model of wl_session_*) -----
+    def open_decode_session(self, capacity: Optional[int] = None, **generate_kwargs) -> "OracleDecodeSession":
+        return OracleDecodeSession(self, capacity or getattr(self, "max_streams", 8), **generate_kwargs)
+
     # -- ctranslate2.models.Whisper.detect_language ----------------------------------------
     def detect_language(self, features) -> List[List[Tuple[str, float]]]:
         if not self.is_multilingual:
@@ -179,3 +183,66 @@ class OracleWhisper:
             attn = np.stack([cross[l][0, h].numpy() for (l, h) in heads])
             out.append(AlignmentResult(oalign.alignment_from_attention(attn, n0, nf, median_filter_width), tok_probs))
         return out
+
+
+class OracleDecodeSession:
+    """CPU model of the engine's decode session (include/wlb200.h, wl_session_*) for the host-side tests: a stream's
+    hypotheses are what ``generate`` returns for it alone (streams are independent), and it occupies its index for as
+    many token steps as that decode took after the (prefilled) prompt.  TEST INFRASTRUCTURE like the rest of oracle/."""
+
+    def __init__(self, engine: OracleWhisper, capacity: int, **kw):
+        if int(kw.get("beam_size", 5)) == 1 and kw.get("sampling_topk", 1) != 1 and kw.get("sampling_temperature", 0) > 0:
+            raise ValueError("a decode session does not sample")
+        self.engine, self.capacity = engine, int(capacity)
+        self.kw = {k: v for k, v in kw.items() if k not in ("max_length", "max_length_per_stream")}
+        self._res: Dict[int, GenerationResult] = {}
+        self._left: Dict[int, int] = {}
+        self.steps = 0
+        self.runs = 0
+        self.closed = False
+
+    @property
+    def live(self) -> int:
+        return len(self._res)
+
+    def free_indices(self) -> List[int]:
+        return [i for i in range(self.capacity) if i not in self._res]
+
+    def admit(self, features, prompts, max_lengths, indices=None) -> List[int]:
+        free = self.free_indices()
+        if indices is None:
+            if len(prompts) > len(free):
+                raise RuntimeError(f"admit: {len(prompts)} streams for {len(free)} free indices")
+            indices = free[:len(prompts)]
+        for i, f, p, ml in zip(indices, features, prompts, max_lengths):
+            r = self.engine.generate(f, [list(p)], max_length=int(ml), **self.kw)[0]
+            self._res[i] = r
+            self._left[i] = max(1, int(r.steps) - (len(p) - 1))
+        return list(indices)
+
+    def run(self, max_steps: int = 16, break_on_finish: bool = True) -> List[int]:
+        self.runs += 1
+        ran = 0
+        while ran < max_steps and any(v > 0 for v in self._left.values()):
+            ran += 1
+            newly = False
+            for i in self._left:
+                if self._left[i] > 0:
+                    self._left[i] -= 1
+                    newly = newly or self._left[i] == 0
+            if newly and break_on_finish:
+                break
+        self.steps += ran
+        self.last_steps = ran
+        return sorted(i for i, v in self._left.items() if v == 0)
+
+    def collect(self, index: int) -> GenerationResult:
+        if self._left.get(index, 1) != 0:
+            raise RuntimeError(f"stream index {index} has not finished")
+        del self._left[index]
+        return self._res.pop(index)
+
+    def close(self) -> None:
+        self.closed = True
+        self._res.clear()
+        self._left.clear()

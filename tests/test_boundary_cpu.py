@@ -131,7 +131,7 @@ def test_round_scheduler_admits_mid_flight_and_answers_early():
     entered = threading.Event()
     orig_round = type(model.open_session()).round
 
-    sch = RoundScheduler(model, max_batch_size=4)
+    sch = RoundScheduler(model, max_batch_size=4, step_tokens=None)     # window-level rounds (step-level: next test)
 
     def patched_round(self_):
         entered.set()
@@ -152,6 +152,58 @@ def test_round_scheduler_admits_mid_flight_and_answers_early():
     assert r_short.error is None and r_long.error is None
     assert sch.admitted_mid_flight >= 1 and sch.max_in_flight == 2
     assert r_short.finished_at < r_long.finished_at      # answered without waiting for the stream it shared rounds with
+    for r, (segs, _info) in zip((r_long, r_short), ref):
+        assert [s.tokens for s in r.result] == [s.tokens for s in segs]
+        assert [(s.start, s.end) for s in r.result] == [(s.start, s.end) for s in segs]
+
+
+def test_step_scheduler_joins_the_running_decode_loop():
+    """N2, token-step level: a chunk submitted while another stream is in the MIDDLE of its decode loop is admitted into
+    that loop (``TranscribeSession.step_round`` over the engine's decode session) after a few token steps -- it does not
+    wait for the running ``generate`` to end -- and is answered first; results equal the one-shot ``transcribe_batch``.
+    (The oracle engine models the session's timing; ``tests/test_gpu_parity.py`` runs the real one.)"""
+    from whisperlive_b200 import synth
+    from whisperlive_b200.scheduler import BatchRequest, RoundScheduler
+    torch.set_num_threads(4)
+    model = _oracle_model()
+    long_wave, short_wave = synth.speech_like(65.0, seed=50), synth.speech_like(3.0, seed=51)
+
+    class Req(BatchRequest):      # no sampling rungs: the comparison below is token for token
+        def kwargs(self):
+            return dict(super().kwargs(), temperature=[0.0], log_prob_threshold=None)
+    ref = model.transcribe_batch([long_wave, short_wave], [Req(audio=long_wave, use_vad=False, language="en").kwargs()] * 2)
+
+    first_steps_done, short_submitted = threading.Event(), threading.Event()
+    sess_cls = type(model.open_session())
+    orig = sess_cls.step_round
+    seen = {}
+
+    def gated(self_, max_steps=16):
+        seen["session"] = self_
+        out = orig(self_, max_steps)
+        if not first_steps_done.is_set():
+            first_steps_done.set()                   # the long stream has run its first token steps ...
+            short_submitted.wait(30)                 # ... and the short one arrives before the next ones
+        return out
+    sess_cls.step_round = gated
+    sch = RoundScheduler(model, max_batch_size=4, step_tokens=2)
+    try:
+        sch.start()
+        r_long = Req(audio=long_wave, use_vad=False, language="en")
+        sch.submit(r_long)
+        assert first_steps_done.wait(120)
+        r_short = Req(audio=short_wave, use_vad=False, language="en")
+        sch.submit(r_short)
+        short_submitted.set()
+        assert r_short.future.wait(240) and r_long.future.wait(480)
+    finally:
+        sess_cls.step_round = orig
+        sch.stop()
+    assert r_short.error is None and r_long.error is None
+    sess = seen["session"]
+    assert sess.admitted_steps[0] == 0 and any(a > 0 for a in sess.admitted_steps[1:])   # joined a loop that was already running
+    assert sch.admitted_mid_flight >= 1 and sch.max_in_flight == 2
+    assert r_short.finished_at < r_long.finished_at
     for r, (segs, _info) in zip((r_long, r_short), ref):
         assert [s.tokens for s in r.result] == [s.tokens for s in segs]
         assert [(s.start, s.end) for s in r.result] == [(s.start, s.end) for s in segs]

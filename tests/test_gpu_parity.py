@@ -841,3 +841,148 @@ def test_full_size_large_v3_single_stream():
     rescored = _oracle_rescore(orc, oenc, 0, sot_seq, a.sequences_ids[0], kw)
     print(f"generate large-v3 beam 4: {len(a.sequences_ids[0])} tokens, engine score {a.scores[0]:.4f}, oracle score of the same tokens {rescored:.4f}")
     assert abs(rescored - a.scores[0]) < 0.02                                    # measured: 0.0013
+
+
+# --------------------------------------------------------------------------------------- N2: decode session
+def _same_hypotheses(a, b, what):
+    """Two runs of the ENGINE over the same stream.  The decode steps use the same kernels row for row; the batched
+    prefill does not (its GEMM / cross-attention splits depend on how many prompt rows share the pass), so the cached
+    prompt K/V may differ in the last fp16 bit: hypotheses agree, or the two runs sit on a near-tie."""
+    assert abs(a.no_speech_prob - b.no_speech_prob) < 2e-3, what
+    if a.sequences_ids[0] == b.sequences_ids[0]:
+        assert abs(a.scores[0] - b.scores[0]) < 2e-3, (what, a.scores, b.scores)
+    else:
+        print("near-tie between two engine runs:", what, a.scores[0], b.scores[0])
+        assert abs(a.scores[0] - b.scores[0]) < SCORE_TOL, (what, a.sequences_ids[0][:12], b.sequences_ids[0][:12])
+
+
+@pytest.mark.parametrize("name,beam", [("micro.en", 5), ("micro", 4), ("tiny", 1)])
+def test_decode_session_step_level_admission(name, beam):
+    """N2 (include/wlb200.h, wl_session_*): streams admitted into the RUNNING device-side decode loop at different token
+    steps, decoded in bounded slices, collected one by one with their indices refilled -- and one-shot calls
+    (generate / align) interleaved between the slices -- give exactly the hypotheses of a one-shot ``generate`` over the
+    same streams (reference: batches run to completion, whisper_live/batch_inference.py:155-187)."""
+    eng, orc = engine(name, seed=0)
+    dims, sp = eng.dims, orc.spec
+    durs = [6.0, 9.0, 5.0, 12.0, 7.0, 4.0]
+    feats = np.stack([feats_for(dims, d, 60 + i) for i, d in enumerate(durs)])
+    enc_a, enc_b = eng.encode(feats[:4]), eng.encode(feats[4:])
+    views = [enc_a.select([i]) for i in range(4)] + [enc_b.select([i]) for i in range(2)]
+    base = [sp.sot] if not dims.multilingual else [sp.sot, sp.sot + 1, sp.sot + 1 + dims.num_languages + 1]
+    rng = np.random.default_rng(23)
+    prev = lambda n: [sp.timestamp_begin - 3] + rng.integers(256, 40000, n).tolist()
+    prompts = [base, prev(40) + base, base, prev(150) + base, base + [sp.no_timestamps], prev(9) + base]
+    lengths = [2 * 30, 448, 2 * 18, 448, 2 * 25, 2 * 40]
+    kw = dict(beam_size=beam, suppress_tokens=[1, 2, 3], return_scores=True, return_no_speech_prob=True)
+    # reference: one-shot generate, 4 streams per call like the session's capacity (same kernels for every row)
+    ref = eng.generate(enc_a, prompts[:4], max_length=448, max_length_per_stream=lengths[:4], **kw)
+    ref += eng.generate(enc_b.join([views[4], views[5], views[0], views[1]]), prompts[4:] + prompts[:2], max_length=448,
+                        max_length_per_stream=lengths[4:] + lengths[:2], **kw)[:2]
+    sess = eng.open_decode_session(capacity=4, **kw)
+    where, got, joined_at = {}, {}, {}
+    order = [0, 1, 2, 3, 4, 5]
+    queue = list(order)
+
+    def admit(n):
+        take = [queue.pop(0) for _ in range(min(n, len(queue), len(sess.free_indices())))]
+        if take:
+            idx = sess.admit([views[i] for i in take], [prompts[i] for i in take], [lengths[i] for i in take])
+            for i, ix in zip(take, idx):
+                where[ix] = i
+                joined_at[i] = sess.steps
+    admit(2)                                           # streams 0, 1 start the loop
+    for ix in sess.run(max_steps=3):                   # 3 token steps (fewer only if somebody already finished)
+        got[where.pop(ix)] = sess.collect(ix)
+    assert 1 <= sess.last_steps <= 3
+    admit(1)                                           # stream 2 joins a loop that has already run for a few steps
+    # one-shot calls between two slices of the session leave it alone (own decode state + self-attention cache)
+    side = eng.generate(views[5], [prompts[5]], max_length=lengths[5], **kw)[0]
+    if eng.alignment_heads:
+        eng.align(views[0], base, [[300, 301, 302]], [200])
+    guard = 0
+    while sess.live or queue:
+        guard += 1
+        assert guard < 400
+        for ix in sess.run(max_steps=7):
+            got[where.pop(ix)] = sess.collect(ix)
+        admit(4)                                       # refill whatever is free
+    sess.close()
+    assert sorted(got) == order
+    assert joined_at[0] == 0 and joined_at[2] > 0 and all(joined_at[i] > joined_at[2] for i in (4, 5))
+    for i in order:
+        _same_hypotheses(got[i], ref[i], f"{name} beam{beam} stream {i}")
+    _same_hypotheses(side, ref[5], "interleaved one-shot generate")
+    print(f"decode session {name} beam {beam}: joined at steps {joined_at}, lengths {[len(got[i].sequences_ids[0]) for i in order]}, "
+          f"{sess.steps} steps in {sess.runs} slices")
+    enc_a.release(); enc_b.release()
+
+
+def test_decode_session_errors():
+    eng, orc = engine("micro.en", seed=0)
+    dims, sp = eng.dims, orc.spec
+    enc = eng.encode(np.stack([feats_for(dims, 5.0, 1), feats_for(dims, 5.0, 2)]))
+    v0, v1 = enc.select([0]), enc.select([1])
+    with pytest.raises(ValueError):
+        eng.open_decode_session(beam_size=1, sampling_topk=0, sampling_temperature=0.7)
+    sess = eng.open_decode_session(capacity=2, beam_size=5)
+    with pytest.raises(Exception, match="has not finished"):
+        sess.collect(0)
+    (i0,) = sess.admit([v0], [[sp.sot]], [20])
+    with pytest.raises(Exception, match="still holds a stream"):
+        sess.admit([v1], [[sp.sot]], [20], indices=[i0])
+    with pytest.raises(Exception, match="out of range|no room"):
+        sess.admit([v1], [[sp.sot] * 30], [20])
+    (i1,) = sess.admit([v1], [[sp.sot]], [20])          # the failed admission left index 1 free
+    with pytest.raises(RuntimeError):
+        sess.admit([v1], [[sp.sot]], [20])               # no free index
+    done = set()
+    for _ in range(40):
+        done |= set(sess.run(max_steps=4))
+        if len(done) == 2:
+            break
+    assert done == {i0, i1}
+    r = sess.collect(i0)
+    assert 1 <= len(r.sequences_ids[0]) <= 10
+    sess.close()
+    enc.release()
+
+
+def test_step_rounds_equal_transcribe_batch():
+    """The transcriber on step-level rounds (``TranscribeSession.step_round``: streams added while others are in the
+    middle of their decode, multi-window audio, word timestamps) gives the segments of the run-to-completion
+    ``transcribe_batch``."""
+    from whisperlive_b200.feature_extractor import FeatureExtractor
+    from whisperlive_b200.transcriber import B200WhisperModel
+    eng, _ = engine("micro.en", seed=0)
+    dims = eng.dims
+    m = B200WhisperModel("micro.en", engine=eng, hf_tokenizer=build_synthetic_tokenizer(dims.vocab),
+                         feature_extractor=FeatureExtractor(eng, dims.n_mels))
+    audios = [synth.speech_like(33.0, seed=70), synth.speech_like(6.0, seed=71), synth.speech_like(14.0, seed=72),
+              synth.speech_like(8.0, seed=73), synth.speech_like(5.0, seed=74)]
+    kws = [dict(temperature=[0.0], beam_size=5, log_prob_threshold=None, compression_ratio_threshold=None,
+                word_timestamps=(i == 2)) for i in range(5)]
+    ref = m.transcribe_batch(audios, kws)
+    sess = m.open_session()
+    handles = sess.add_streams(audios[:2], kws[:2])
+    results, rounds = {}, 0
+    late = [(2, 2), (4, 3), (6, 4)]                      # (round, stream): admitted while the others are mid-decode
+    while sess.pending() or late:
+        while late and late[0][0] <= rounds:
+            handles += sess.add_streams([audios[late[0][1]]], [kws[late[0][1]]])
+            late.pop(0)
+        sess.step_round(max_steps=5)
+        rounds += 1
+        for e in sess.pop_finished():
+            results[e.handle] = sess.result_of(e)
+        assert rounds < 500
+    sess.close()
+    assert any(a > 0 for a in sess.admitted_steps)       # somebody joined a loop that was already running
+    for h, (segs_ref, _info) in zip(handles, ref):
+        segs, _ = results[h]
+        assert [s.tokens for s in segs] == [s.tokens for s in segs_ref]
+        assert [(s.start, s.end) for s in segs] == [(s.start, s.end) for s in segs_ref]
+        for a, b in zip(segs, segs_ref):
+            assert (a.words is None) == (b.words is None)
+            if a.words is not None:
+                assert [(w.word, w.start, w.end) for w in a.words] == [(w.word, w.start, w.end) for w in b.words]
+    print(f"step rounds: {rounds} rounds, admissions at session steps {sess.admitted_steps}")

@@ -50,7 +50,7 @@ struct wl_ctx {
   std::string err;
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float last_ms[3] = {0, 0, 0};
+  float last_ms[6] = {0, 0, 0, 0, 0, 0};   // [0] mel, [1] encode, [2] generate / session run, [5] session admit (prefill)
   // per-kernel profiling of the dominant decode kernel (bench.py roofline): events around every cross-attention launch
   unsigned* post_bar = nullptr;   // grid-barrier words of the fused split-K consumers
   int prof_cross = 0;
@@ -133,6 +133,24 @@ struct wl_ctx {
   } pf;
   float* stage_f32 = nullptr;   // wl_load_tensor staging (freed by wl_finalize_weights)
   size_t stage_cap = 0;
+  // Decode session (N2, step-level continuous batching): a second decode state + self-attention cache whose stream
+  // indices are admitted, decoded for a bounded number of token steps and collected independently of each other.
+  // One-shot calls (wl_generate / wl_align / wl_detect_language) keep using `ds` / `kcache`, so they may run between two
+  // wl_session_run calls without disturbing the streams in flight.
+  struct Session {
+    bool allocated = false, open = false;
+    int cap = 0, K = 1, Kr = 1, NH = 1, nsplit = 1, use_graph = 1;
+    float length_penalty = 1.f;
+    SearchOpts so;
+    DecodeState ds;
+    __half *kcache = nullptr, *vcache = nullptr;
+    unsigned* mask = nullptr;
+    int* idx_dev = nullptr;
+    std::vector<int> hp, meta;          // host shadows: prompts [cap][T_MAX], per-stream metadata [10][cap]
+    std::vector<char> used, finished;   // index holds an admitted stream / that stream has finished decoding
+    int live = 0;                       // admitted and still decoding
+    long steps = 0, runs = 0, admitted = 0;
+  } sess;
 };
 
 #define API_BEGIN(ctx)                                          \
@@ -176,6 +194,25 @@ static void ensure_host(wl_ctx* c, size_t n_int, size_t n_flt) {
     WL_CUDA(cudaMallocHost((void**)&c->h_flt, n_flt * sizeof(float)));
     c->h_flt_cap = n_flt;
   }
+}
+
+// device-resident decode state for Bm streams x Km rows (one per context, plus one per decode session)
+static void alloc_decode_state(wl_ctx* c, DecodeState& s) {
+  const size_t R = c->Rm, B = c->Bm;
+  s.tok_in = dalloc<int>(c, R); s.pos = dalloc<int>(c, R); s.active = dalloc<int>(c, R); s.cum = dalloc<float>(c, R);
+  s.gen_len = dalloc<int>(c, R); s.last_ts = dalloc<int>(c, R); s.row_done = dalloc<int>(c, R);
+  s.hist = dalloc<int>(c, R * T_MAX); s.src = dalloc<short>(c, R * T_MAX);
+  s.cand_val = dalloc<float>(c, R * MAX_CAND); s.cand_tok = dalloc<int>(c, R * MAX_CAND);
+  s.nospeech_row = dalloc<float>(c, R);
+  s.slot = dalloc<int>(c, B); s.prompt = dalloc<int>(c, B * T_MAX); s.prompt_len = dalloc<int>(c, B);
+  s.fed = dalloc<int>(c, B); s.sot_index = dalloc<int>(c, B); s.use_ts = dalloc<int>(c, B); s.n_new = dalloc<int>(c, B);
+  s.step = dalloc<int>(c, B); s.done = dalloc<int>(c, B); s.n_alive = dalloc<int>(c, B); s.no_speech = dalloc<float>(c, B);
+  s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
+  s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
+  s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
+  s.seed = dalloc<unsigned>(c, 1); s.steps_left = dalloc<int>(c, 1);
+  s.pre_n = dalloc<int>(c, B); s.pre_last = dalloc<int>(c, B); s.pre_penult = dalloc<int>(c, B); s.pre_lts = dalloc<int>(c, B);
+  s.brk = dalloc<int>(c, 2);
 }
 
 // ------------------------------------------------------------------------------------------ init
@@ -262,6 +299,7 @@ extern "C" float wl_last_device_ms(wl_ctx* c, int32_t which) {
   if (which >= 0 && which < 3) return c->last_ms[which];
   if (which == 3) return c->prof_cross_n > 0 ? (float)(c->prof_cross_ms / (double)c->prof_cross_n) : -1.f;   // avg ms per cross-attention launch
   if (which == 4) return (float)c->prof_cross_n;
+  if (which == 5) return c->last_ms[5];   // last wl_session_admit (upload + batched prefill + init)
   return -1.f;
 }
 extern "C" int wl_profile_cross_attn(wl_ctx* c, int32_t enable) {
@@ -489,21 +527,7 @@ extern "C" int wl_finalize_weights(wl_ctx* c) {
     c->align_heads_dev = dalloc<int>(c, c->align_heads.size());
     WL_CUDA(cudaMemcpy(c->align_heads_dev, c->align_heads.data(), c->align_heads.size() * 4, cudaMemcpyHostToDevice));
   }
-  DecodeState& s = c->ds;
-  const size_t B = c->Bm;
-  s.tok_in = dalloc<int>(c, R); s.pos = dalloc<int>(c, R); s.active = dalloc<int>(c, R); s.cum = dalloc<float>(c, R);
-  s.gen_len = dalloc<int>(c, R); s.last_ts = dalloc<int>(c, R); s.row_done = dalloc<int>(c, R);
-  s.hist = dalloc<int>(c, R * T_MAX); s.src = dalloc<short>(c, R * T_MAX);
-  s.cand_val = dalloc<float>(c, R * MAX_CAND); s.cand_tok = dalloc<int>(c, R * MAX_CAND);
-  s.nospeech_row = dalloc<float>(c, R);
-  s.slot = dalloc<int>(c, B); s.prompt = dalloc<int>(c, B * T_MAX); s.prompt_len = dalloc<int>(c, B);
-  s.fed = dalloc<int>(c, B); s.sot_index = dalloc<int>(c, B); s.use_ts = dalloc<int>(c, B); s.n_new = dalloc<int>(c, B);
-  s.step = dalloc<int>(c, B); s.done = dalloc<int>(c, B); s.n_alive = dalloc<int>(c, B); s.no_speech = dalloc<float>(c, B);
-  s.hyp_count = dalloc<int>(c, B); s.hyp_cum = dalloc<float>(c, B * MAX_HYPS); s.hyp_len = dalloc<int>(c, B * MAX_HYPS);
-  s.hyp_tok = dalloc<int>(c, B * MAX_HYPS * T_MAX); s.steps_run = dalloc<int>(c, B); s.n_done = dalloc<int>(c, 1);
-  s.force_len = dalloc<int>(c, B); s.force_prob = dalloc<float>(c, B * T_MAX);
-  s.seed = dalloc<unsigned>(c, 1); s.steps_left = dalloc<int>(c, 1);
-  s.pre_n = dalloc<int>(c, B); s.pre_last = dalloc<int>(c, B); s.pre_penult = dalloc<int>(c, B); s.pre_lts = dalloc<int>(c, B);
+  alloc_decode_state(c, c->ds);
   WL_CUDA(cudaDeviceSynchronize());
   c->finalized = true;
   API_END(c)
@@ -995,19 +1019,22 @@ struct PfRows {
   int NV = 0;
 };
 
+// index (optional, [B]): the decode-state index of list entry b (a decode session admits streams into arbitrary free
+// indices; a one-shot call uses b itself) -- selects the hp row and the cache row the positions are written to.
 static PfRows pf_rows(int B, int Kr, const int* toks, const int* tok_off /*B+1 or null: hp rows of T_MAX*/, const int* ntok,
-                      const int32_t* slots) {
+                      const int32_t* slots, const int32_t* index = nullptr) {
   PfRows r;
   r.rowbase.assign(B, 0);
   for (int b = 0; b < B; ++b) {
     r.rowbase[b] = (int)r.tok.size();
     const int n = ntok[b], n8 = (n + 7) / 8 * 8;
-    const int* src = tok_off ? toks + tok_off[b] : toks + (size_t)b * T_MAX;
+    const int sb = index ? index[b] : b;
+    const int* src = tok_off ? toks + tok_off[b] : toks + (size_t)sb * T_MAX;
     for (int i = 0; i < n8; ++i) {
       r.tok.push_back(i < n ? src[i] : 0);
       r.pos.push_back(i < n ? i : 0);
       r.act.push_back(i < n ? 1 : 0);
-      r.wrow.push_back(b * Kr);
+      r.wrow.push_back(sb * Kr);
       r.row_b.push_back(b);
     }
     for (int g = 0; g < n8 / 8; ++g) r.vslot.push_back(slots[b]);
@@ -1126,16 +1153,22 @@ static void pf_row_probs(wl_ctx* c, const std::vector<int>& sel, const std::vect
 // K8: all prompt positions but the last of every stream through the decoder stack in one pass.  hp = prompts [B][T_MAX]
 // (pinned host), P / sot / slots per stream.  Leaves the self-attention cache filled for positions 0 .. P-2 in the
 // stream's first decode row (b * Kr) and the no-speech probability of streams whose sot lies inside the prompt.
-static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* P, const int* sot, const int32_t* slots) {
-  WL_CUDA(cudaMemsetAsync(c->ds.no_speech, 0, B * sizeof(float), c->st));
+static void prefill_forward(wl_ctx* c, int B, int Kr, const int* hp, const int* P, const int* sot, const int32_t* slots,
+                            const int32_t* index = nullptr) {
+  // (with `index`: hp rows and P / sot columns are addressed by state index, list entry b is state index index[b])
+  auto at = [&](int b) { return index ? index[b] : b; };
+  if (!index) WL_CUDA(cudaMemsetAsync(c->ds.no_speech, 0, B * sizeof(float), c->st));
+  else for (int b = 0; b < B; ++b) WL_CUDA(cudaMemsetAsync(c->ds.no_speech + index[b], 0, sizeof(float), c->st));
   std::vector<int> ntok(B);
-  for (int b = 0; b < B; ++b) ntok[b] = P[b] - 1;
-  const PfRows r = pf_rows(B, Kr, hp, nullptr, ntok.data(), slots);
+  for (int b = 0; b < B; ++b) ntok[b] = P[at(b)] - 1;
+  const PfRows r = pf_rows(B, Kr, hp, nullptr, ntok.data(), slots, index);
   if (r.M == 0) return;
   pf_stack(c, r, false);
   std::vector<int> sel, tgt, oidx;
-  for (int b = 0; b < B; ++b)
-    if (sot[b] >= 0 && sot[b] < P[b] - 1) { sel.push_back(r.rowbase[b] + sot[b]); tgt.push_back(c->cfg.no_speech); oidx.push_back(b); }
+  for (int b = 0; b < B; ++b) {
+    const int sb = at(b);
+    if (sot[sb] >= 0 && sot[sb] < P[sb] - 1) { sel.push_back(r.rowbase[b] + sot[sb]); tgt.push_back(c->cfg.no_speech); oidx.push_back(sb); }
+  }
   if (!sel.empty()) pf_row_probs(c, sel, tgt, oidx, c->ds.no_speech);
 }
 
@@ -1146,6 +1179,60 @@ static VocabIds vocab_ids(wl_ctx* c) {
   return v;
 }
 
+// Per-stream metadata of a decode call (column b of the [10][B] table `meta`; tokens into hp_row[T_MAX]).  Returns the
+// decode steps the stream may need without prefill; *n_new_out = the new tokens it may emit.
+static int stream_meta(wl_ctx* c, int b, int slot, const int32_t* prompt, int P, int ml, bool forced, int* hp_row, int* meta, int col,
+                       int ncol, int* n_new_out) {
+  WL_CHECK(P >= 1 && P <= T_MAX, WL_ERR_ARG, "stream %d: prompt length %d out of range", b, P);
+  WL_CHECK(slot >= 0 && slot < c->NS && c->slot_used[slot], WL_ERR_ARG, "stream %d: bad encoder slot %d", b, slot);
+  int sot = -1;
+  for (int i = 0; i < P; ++i) {
+    const int t = prompt[i];
+    WL_CHECK(t >= 0 && t < c->V, WL_ERR_ARG, "stream %d: token id %d out of range", b, t);
+    hp_row[i] = t;
+    if (t == c->cfg.sot && sot < 0) sot = i;
+  }
+  int n_new = 0, steps = P;
+  if (!forced) {
+    WL_CHECK(ml >= 2 && ml <= T_MAX, WL_ERR_ARG, "stream %d: max_length %d out of range", b, ml);
+    n_new = std::min(ml / 2, ml - P);
+    WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, ml);
+    steps = P - 1 + n_new;
+  }
+  // end of the sot sequence = CT2's prompt length: sot, then every following id in [sot, no_timestamps]
+  // (language, task, notimestamps); the tokens after it are a prefix that counts as sampled text
+  int sb = P;
+  if (sot >= 0) {
+    sb = sot + 1;
+    while (sb < P && prompt[sb] >= c->cfg.sot && prompt[sb] <= c->cfg.no_timestamps) ++sb;
+  }
+  const int npre = P - sb;
+  int lts = -1;
+  for (int i = sb; i < P; ++i)
+    if (prompt[i] >= c->cfg.timestamp_begin) lts = prompt[i];
+  meta[0 * ncol + col] = slot;
+  meta[1 * ncol + col] = P;
+  meta[2 * ncol + col] = sot;
+  meta[3 * ncol + col] = sb >= 1 ? prompt[sb - 1] != c->cfg.no_timestamps : 1;
+  meta[4 * ncol + col] = n_new;
+  meta[5 * ncol + col] = forced ? P : 0;
+  meta[6 * ncol + col] = forced ? 0 : npre;
+  meta[7 * ncol + col] = npre >= 1 ? prompt[P - 1] : -1;
+  meta[8 * ncol + col] = npre >= 2 ? prompt[P - 2] : -1;
+  meta[9 * ncol + col] = forced ? -1 : lts;
+  if (n_new_out) *n_new_out = n_new;
+  return steps;
+}
+
+// prompts [B][T_MAX] + the [10][B] metadata table (pinned host) -> the device state
+static void upload_state_tables(wl_ctx* c, const int* hp, const int* meta, int B) {
+  const DecodeState& s = c->ds;
+  cudaStream_t st = c->st;
+  WL_CUDA(cudaMemcpyAsync(s.prompt, hp, (size_t)B * T_MAX * 4, cudaMemcpyHostToDevice, st));
+  int* dst[10] = {s.slot, s.prompt_len, s.sot_index, s.use_ts, s.n_new, s.force_len, s.pre_n, s.pre_last, s.pre_penult, s.pre_lts};
+  for (int k = 0; k < 10; ++k) WL_CUDA(cudaMemcpyAsync(dst[k], meta + (size_t)k * B, B * 4, cudaMemcpyHostToDevice, st));
+}
+
 // upload prompts & per-stream metadata; returns max steps
 static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t* prompts, const int32_t* off, int max_length,
                           bool forced, const int32_t* max_len_ps = nullptr, int* max_new_out = nullptr) {
@@ -1154,64 +1241,93 @@ static int upload_streams(wl_ctx* c, const int32_t* slots, int B, const int32_t*
   int* meta = c->h_int + (size_t)B * T_MAX;  // slot, len, sot_index, use_ts, n_new, force_len, pre_n, pre_last, pre_penult, pre_lts
   int max_steps = 0, max_new = 0;
   for (int b = 0; b < B; ++b) {
-    const int P = off[b + 1] - off[b];
-    WL_CHECK(P >= 1 && P <= T_MAX, WL_ERR_ARG, "stream %d: prompt length %d out of range", b, P);
-    WL_CHECK(slots[b] >= 0 && slots[b] < c->NS && c->slot_used[slots[b]], WL_ERR_ARG, "stream %d: bad encoder slot %d", b, slots[b]);
-    int sot = -1;
-    for (int i = 0; i < P; ++i) {
-      const int t = prompts[off[b] + i];
-      WL_CHECK(t >= 0 && t < c->V, WL_ERR_ARG, "stream %d: token id %d out of range", b, t);
-      hp[(size_t)b * T_MAX + i] = t;
-      if (t == c->cfg.sot && sot < 0) sot = i;
-    }
     int n_new = 0;
-    if (!forced) {
-      const int ml = max_len_ps ? max_len_ps[b] : max_length;
-      WL_CHECK(ml >= 2 && ml <= T_MAX, WL_ERR_ARG, "stream %d: max_length %d out of range", b, ml);
-      n_new = std::min(ml / 2, ml - P);
-      WL_CHECK(n_new >= 1, WL_ERR_ARG, "stream %d: prompt of %d tokens leaves no room under max_length %d", b, P, ml);
-      max_steps = std::max(max_steps, P - 1 + n_new);
-      max_new = std::max(max_new, n_new);
-    } else {
-      max_steps = std::max(max_steps, P);
-    }
-    // end of the sot sequence = CT2's prompt length: sot, then every following id in [sot, no_timestamps]
-    // (language, task, notimestamps); the tokens after it are a prefix that counts as sampled text
-    int sb = P;
-    if (sot >= 0) {
-      sb = sot + 1;
-      while (sb < P && prompts[off[b] + sb] >= c->cfg.sot && prompts[off[b] + sb] <= c->cfg.no_timestamps) ++sb;
-    }
-    const int npre = P - sb;
-    int lts = -1;
-    for (int i = sb; i < P; ++i)
-      if (prompts[off[b] + i] >= c->cfg.timestamp_begin) lts = prompts[off[b] + i];
-    meta[0 * B + b] = slots[b];
-    meta[1 * B + b] = P;
-    meta[2 * B + b] = sot;
-    meta[3 * B + b] = sb >= 1 ? prompts[off[b] + sb - 1] != c->cfg.no_timestamps : 1;
-    meta[4 * B + b] = n_new;
-    meta[5 * B + b] = forced ? P : 0;
-    meta[6 * B + b] = forced ? 0 : npre;
-    meta[7 * B + b] = npre >= 1 ? prompts[off[b] + P - 1] : -1;
-    meta[8 * B + b] = npre >= 2 ? prompts[off[b] + P - 2] : -1;
-    meta[9 * B + b] = forced ? -1 : lts;
+    const int steps = stream_meta(c, b, slots[b], prompts + off[b], off[b + 1] - off[b], max_len_ps ? max_len_ps[b] : max_length,
+                                  forced, hp + (size_t)b * T_MAX, meta, b, B, &n_new);
+    max_steps = std::max(max_steps, steps);
+    max_new = std::max(max_new, n_new);
   }
-  const DecodeState& s = c->ds;
-  cudaStream_t st = c->st;
-  WL_CUDA(cudaMemcpyAsync(s.prompt, hp, (size_t)B * T_MAX * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.slot, meta + 0 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.prompt_len, meta + 1 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.sot_index, meta + 2 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.use_ts, meta + 3 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.n_new, meta + 4 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.force_len, meta + 5 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.pre_n, meta + 6 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.pre_last, meta + 7 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.pre_penult, meta + 8 * B, B * 4, cudaMemcpyHostToDevice, st));
-  WL_CUDA(cudaMemcpyAsync(s.pre_lts, meta + 9 * B, B * 4, cudaMemcpyHostToDevice, st));
+  upload_state_tables(c, hp, meta, B);
   if (max_new_out) *max_new_out = max_new;
   return max_steps;
+}
+
+// finished hypotheses of one stream (device order) -> the NH best by cum_logprob / len^length_penalty, like CT2
+static void emit_hyps(int NH, float length_penalty, int count, const int* h_len, const float* h_cum, const int* h_tok, int32_t* out_ids,
+                      int32_t* out_len, float* out_score) {
+  const int cnt = std::min(count, MAX_HYPS);
+  std::vector<int> order(cnt);
+  std::vector<float> score(cnt);
+  for (int i = 0; i < cnt; ++i) {
+    order[i] = i;
+    score[i] = length_penalty == 0.f ? h_cum[i] : h_cum[i] / powf((float)std::max(h_len[i], 1), length_penalty);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return score[a] > score[bb]; });
+  for (int hh = 0; hh < NH; ++hh) {
+    int* dst = out_ids + (size_t)hh * T_MAX;
+    if (hh < cnt) {
+      const int i = order[hh];
+      memcpy(dst, h_tok + (size_t)i * T_MAX, h_len[i] * sizeof(int));
+      out_len[hh] = h_len[i];
+      out_score[hh] = score[i];
+    } else {
+      out_len[hh] = -1;
+      out_score[hh] = 0.f;
+    }
+  }
+}
+
+// The captured decode step for one call shape (cached per context).  loop_graph: a conditional WHILE node whose body is
+// the step + loop_condition (the whole token loop is one launch); else the plain step.  `tag` separates the graphs of the
+// one-shot state ("g") from those of the decode session ("s"): the captures bake the state's device pointers in.
+static cudaGraphExec_t decode_graph(wl_ctx* c, const char* tag, int B, int Kr, int K, const SearchOpts& so, const VocabIds& vi,
+                                    int nsplit, bool loop_graph, long* kernels) {
+  cudaStream_t st = c->st;
+  char key[160];
+  snprintf(key, sizeof(key), "%s/%d/%d/%d/%d/%d/%d/%d/%08x/%d", tag, B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
+           so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
+  GraphEntry& ge = c->graphs[key];
+  if (!ge.exec) {
+    const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count();
+    cudaGraph_t g = nullptr, cap = nullptr;
+    if (loop_graph) {
+      WL_CUDA(cudaGraphCreate(&g, 0));
+      cudaGraphConditionalHandle h;
+      WL_CUDA(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.conditional.handle = h;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      WL_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      WL_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(c, B, Kr, so, vi, nsplit, false);
+        loop_condition(st, c->ds, h, B);
+      } catch (...) {
+        cudaStreamEndCapture(st, &cap);
+        cudaGraphDestroy(g);
+        throw;
+      }
+      WL_CUDA(cudaStreamEndCapture(st, &cap));
+    } else {
+      WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(c, B, Kr, so, vi, nsplit, false);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        throw;
+      }
+      WL_CUDA(cudaStreamEndCapture(st, &g));
+    }
+    ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count() - before;
+    c->capture_counted += ge.kernels;
+    WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
+    cudaGraphDestroy(g);
+  }
+  *kernels = ge.kernels;
+  return ge.exec;
 }
 
 extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int32_t* prompts, const int32_t* prompt_off,
@@ -1274,51 +1390,7 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
   long graph_kernels = 0;
   bool is_loop = false;
   if (o->use_cuda_graph) {
-    char key[160];
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%d/%d/%08x/%d", B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
-             so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
-    GraphEntry& ge = c->graphs[key];
-    if (!ge.exec) {
-      const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count();
-      cudaGraph_t g = nullptr, cap = nullptr;
-      if (loop_graph) {
-        WL_CUDA(cudaGraphCreate(&g, 0));
-        cudaGraphConditionalHandle h;
-        WL_CUDA(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
-        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
-        np.conditional.handle = h;
-        np.conditional.type = cudaGraphCondTypeWhile;
-        np.conditional.size = 1;
-        cudaGraphNode_t node;
-        WL_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &np));
-        cudaGraph_t body = np.conditional.phGraph_out[0];
-        WL_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-        try {
-          decode_step(c, B, Kr, so, vi, nsplit, false);
-          loop_condition(st, c->ds, h, B);
-        } catch (...) {
-          cudaStreamEndCapture(st, &cap);
-          cudaGraphDestroy(g);
-          throw;
-        }
-        WL_CUDA(cudaStreamEndCapture(st, &cap));
-      } else {
-        WL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        try {
-          decode_step(c, B, Kr, so, vi, nsplit, false);
-        } catch (...) {
-          cudaStreamEndCapture(st, &g);
-          throw;
-        }
-        WL_CUDA(cudaStreamEndCapture(st, &g));
-      }
-      ge.kernels = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count() - before;
-      c->capture_counted += ge.kernels;
-      WL_CUDA(cudaGraphInstantiate(&ge.exec, g, 0));
-      cudaGraphDestroy(g);
-    }
-    exec = ge.exec;
-    graph_kernels = ge.kernels;
+    exec = decode_graph(c, "g", B, Kr, K, so, vi, nsplit, loop_graph, &graph_kernels);
     is_loop = loop_graph;
   }
   ensure_host(c, (size_t)B * (T_MAX + 16) + (size_t)B * MAX_HYPS * (T_MAX + 2) + 64, (size_t)B * (MAX_HYPS + 2));
@@ -1374,33 +1446,234 @@ extern "C" int wl_generate(wl_ctx* c, const int32_t* slots, int32_t B, const int
     if (FILE* f = fopen(c->tl_path.c_str(), "wb")) { fwrite(h.data() + 1, 8, n, f); fclose(f); }
     WL_CUDA(cudaMemset(c->tl_dev, 0, 8));
   }
-  const int NH = o->num_hypotheses;
   for (int b = 0; b < B; ++b) {
-    const int cnt = std::min(h_cnt[b], MAX_HYPS);
-    std::vector<int> order(cnt);
-    std::vector<float> score(cnt);
-    for (int i = 0; i < cnt; ++i) {
-      order[i] = i;
-      const int len = h_len[b * MAX_HYPS + i];
-      score[i] = o->length_penalty == 0.f ? h_cum[b * MAX_HYPS + i]
-                                          : h_cum[b * MAX_HYPS + i] / powf((float)std::max(len, 1), o->length_penalty);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return score[a] > score[bb]; });
-    for (int hh = 0; hh < NH; ++hh) {
-      int* dst = out_ids + ((size_t)b * NH + hh) * T_MAX;
-      if (hh < cnt) {
-        const int i = order[hh];
-        const int len = h_len[b * MAX_HYPS + i];
-        memcpy(dst, h_tok + ((size_t)b * MAX_HYPS + i) * T_MAX, len * sizeof(int));
-        out_len[b * NH + hh] = len;
-        out_score[b * NH + hh] = score[i];
-      } else {
-        out_len[b * NH + hh] = -1;
-        out_score[b * NH + hh] = 0.f;
-      }
-    }
+    emit_hyps(o->num_hypotheses, o->length_penalty, h_cnt[b], h_len + (size_t)b * MAX_HYPS, h_cum + (size_t)b * MAX_HYPS,
+              h_tok + (size_t)b * MAX_HYPS * T_MAX, out_ids + (size_t)b * o->num_hypotheses * T_MAX, out_len + (size_t)b * o->num_hypotheses,
+              out_score + (size_t)b * o->num_hypotheses);
     if (out_no_speech) out_no_speech[b] = h_ns[b];
     if (out_steps) out_steps[b] = h_steps[b];
+  }
+  API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------ N2 decode session
+// Step-level continuous batching (replaces the run-to-completion batches of the reference's BatchInferenceWorker,
+// whisper_live/batch_inference.py:155-187, :259, :334-339): the decode state has `cap` stream indices; a stream is
+// admitted into a free index at any token-step boundary (prompt prefilled in one pass, K8), the device-side loop runs
+// for a bounded number of steps or until some stream finishes, and a finished stream is collected -- and its index
+// refilled -- while the others keep decoding.  Idle indices carry done = 1: every kernel of the step skips them.
+struct SessScope {   // the session's state / cache / suppress mask stand in for the one-shot ones inside a session call
+  wl_ctx* c;
+  explicit SessScope(wl_ctx* ctx) : c(ctx) { swap(); }
+  ~SessScope() { swap(); }
+  void swap() {
+    std::swap(c->ds, c->sess.ds);
+    std::swap(c->kcache, c->sess.kcache);
+    std::swap(c->vcache, c->sess.vcache);
+    std::swap(c->suppress_mask, c->sess.mask);
+  }
+};
+
+extern "C" int wl_session_open(wl_ctx* c, const wl_gen_opts* o, int32_t capacity) {
+  API_BEGIN(c)
+  WL_CHECK(c->finalized, WL_ERR_STATE, "weights not finalized");
+  WL_CHECK(o, WL_ERR_ARG, "wl_session_open: null options");
+  wl_ctx::Session& ss = c->sess;
+  WL_CHECK(!ss.open || ss.live == 0, WL_ERR_STATE, "wl_session_open: %d streams of the open session are still decoding", ss.live);
+  WL_CHECK(capacity >= 1 && capacity <= c->Bm, WL_ERR_ARG, "wl_session_open: capacity %d exceeds max_streams=%d", capacity, c->Bm);
+  WL_CHECK(o->beam_size >= 1 && o->num_hypotheses >= 1, WL_ERR_ARG, "wl_session_open: beam_size / num_hypotheses must be >= 1");
+  const int K = o->beam_size, Kr = K > 1 ? K : o->num_hypotheses;
+  WL_CHECK(Kr <= c->Km, WL_ERR_ARG, "wl_session_open: %d rows per stream exceed max_beam=%d", Kr, c->Km);
+  WL_CHECK(K == 1 || o->num_hypotheses <= MAX_HYPS, WL_ERR_ARG, "too many hypotheses");
+  // sampling draws are keyed by (call seed, batch position): a session has neither, so the temperature-fallback rungs stay
+  // on wl_generate (the transcriber routes them there)
+  WL_CHECK(!(K == 1 && o->sampling_topk == 0 && o->sampling_temperature > 0.f), WL_ERR_ARG, "wl_session_open: sampling is not supported in a decode session");
+  if (!ss.allocated) {
+    alloc_decode_state(c, ss.ds);
+    ss.kcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
+    ss.vcache = dalloc<__half>(c, (size_t)c->Ld * c->cache_layer_stride, false);
+    ss.mask = dalloc<unsigned>(c, (c->V + 31) / 32 + 1);
+    ss.idx_dev = dalloc<int>(c, c->Bm);
+    ss.allocated = true;
+  }
+  ss.cap = capacity; ss.K = K; ss.Kr = Kr; ss.NH = o->num_hypotheses; ss.length_penalty = o->length_penalty;
+  ss.use_graph = o->use_cuda_graph;
+  SearchOpts& so = ss.so;
+  so.beam = K; so.rows_per_stream = Kr;
+  so.max_cand = std::max(1, std::min(MAX_HYPS, (int)lroundf(K * o->patience)));
+  so.suppress_blank = o->suppress_blank; so.max_initial_ts = o->max_initial_timestamp_index;
+  so.sampling = 0; so.temperature = o->sampling_temperature; so.seed = o->seed; so.suppress_mask = ss.mask;
+  ss.nsplit = cross_attn_pick_nsplit(capacity, c->H, c->num_sms, Kr);
+  const int nwords = (c->V + 31) / 32 + 1;
+  std::vector<unsigned> mask(nwords, 0u);
+  for (int i = 0; i < o->n_suppress; ++i) {
+    const int t = o->suppress_tokens[i];
+    if (t >= 0 && t < c->V) mask[t >> 5] |= 1u << (t & 31);
+  }
+  const int cap = capacity, R = cap * Kr;
+  ss.hp.assign((size_t)cap * T_MAX, 0);
+  ss.meta.assign((size_t)10 * cap, 0);
+  for (int b = 0; b < cap; ++b) { ss.meta[1 * cap + b] = 1; ss.meta[2 * cap + b] = -1; ss.meta[4 * cap + b] = 1; }   // harmless idle values
+  ss.used.assign(cap, 0);
+  ss.finished.assign(cap, 0);
+  ss.live = 0;
+  cudaStream_t st = c->st;
+  const DecodeState& s = ss.ds;
+  std::vector<int> ones(cap, 1);
+  const int nd = cap, brk0[2] = {0, 0};
+  const unsigned seed_host = o->seed;
+  WL_CUDA(cudaMemcpyAsync(ss.mask, mask.data(), nwords * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.done, ones.data(), cap * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemsetAsync(s.active, 0, (size_t)R * 4, st));
+  WL_CUDA(cudaMemsetAsync(s.hyp_count, 0, (size_t)cap * 4, st));
+  WL_CUDA(cudaMemcpyAsync(s.n_done, &nd, 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.brk, brk0, 8, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaMemcpyAsync(s.seed, &seed_host, 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+  ss.open = true;
+  API_END(c)
+}
+
+extern "C" int wl_session_admit(wl_ctx* c, int32_t n, const int32_t* index, const int32_t* slots, const int32_t* prompts,
+                                const int32_t* prompt_off, const int32_t* max_length) {
+  API_BEGIN(c)
+  wl_ctx::Session& ss = c->sess;
+  WL_CHECK(ss.open, WL_ERR_STATE, "wl_session_admit: no open session");
+  WL_CHECK(n >= 1 && index && slots && prompts && prompt_off && max_length, WL_ERR_ARG, "wl_session_admit: bad arguments");
+  const int cap = ss.cap;
+  for (int i = 0; i < n; ++i) {
+    WL_CHECK(index[i] >= 0 && index[i] < cap, WL_ERR_ARG, "wl_session_admit: index %d outside the session capacity %d", index[i], cap);
+    WL_CHECK(!ss.used[index[i]], WL_ERR_STATE, "wl_session_admit: index %d still holds a stream", index[i]);
+    for (int j = 0; j < i; ++j) WL_CHECK(index[j] != index[i], WL_ERR_ARG, "wl_session_admit: index %d listed twice", index[i]);
+  }
+  // validate + stage everything before touching the session (a bad prompt must not leave a half-admitted stream)
+  std::vector<int> hp = ss.hp, meta = ss.meta;
+  for (int i = 0; i < n; ++i)
+    stream_meta(c, i, slots[i], prompts + prompt_off[i], prompt_off[i + 1] - prompt_off[i], max_length[i], false,
+                hp.data() + (size_t)index[i] * T_MAX, meta.data(), index[i], cap, nullptr);
+  ss.hp.swap(hp);
+  ss.meta.swap(meta);
+  ensure_host(c, (size_t)cap * (T_MAX + 16) + n, 16);
+  int* php = c->h_int;
+  int* pmeta = php + (size_t)cap * T_MAX;
+  int* pidx = pmeta + (size_t)10 * cap;
+  memcpy(php, ss.hp.data(), ss.hp.size() * 4);
+  memcpy(pmeta, ss.meta.data(), ss.meta.size() * 4);
+  memcpy(pidx, index, (size_t)n * 4);
+  SessScope scope(c);
+  cudaStream_t st = c->st;
+  WL_CUDA(cudaEventRecord(c->ev0, st));
+  // the tables of the streams in flight are rewritten with the values they already hold (nothing runs between two calls)
+  upload_state_tables(c, php, pmeta, cap);
+  WL_CUDA(cudaMemcpyAsync(ss.idx_dev, pidx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  WL_CUDA(cudaStreamSynchronize(st));
+  prefill_forward(c, n, ss.Kr, ss.hp.data(), ss.meta.data() + 1 * cap, ss.meta.data() + 2 * cap, slots, index);
+  decode_init(st, c->ds, ss.so, vocab_ids(c), n, cap * ss.Kr, 1, ss.idx_dev);
+  WL_CUDA(cudaEventRecord(c->ev1, st));
+  WL_CUDA(cudaStreamSynchronize(st));
+  WL_CUDA(cudaEventElapsedTime(&c->last_ms[5], c->ev0, c->ev1));
+  for (int i = 0; i < n; ++i) { ss.used[index[i]] = 1; ss.finished[index[i]] = 0; }
+  ss.live += n;
+  ss.admitted += n;
+  API_END(c)
+}
+
+extern "C" int wl_session_run(wl_ctx* c, int32_t max_steps, int32_t break_on_finish, int32_t* done_out, int32_t* steps_ran) {
+  API_BEGIN(c)
+  wl_ctx::Session& ss = c->sess;
+  WL_CHECK(ss.open, WL_ERR_STATE, "wl_session_run: no open session");
+  WL_CHECK(max_steps >= 1 && done_out, WL_ERR_ARG, "wl_session_run: bad arguments");
+  const int cap = ss.cap;
+  int ran = 0;
+  c->last_ms[2] = 0.f;
+  if (ss.live > 0) {
+    SessScope scope(c);
+    cudaStream_t st = c->st;
+    const VocabIds vi = vocab_ids(c);
+    ensure_host(c, (size_t)cap + 16, 16);
+    int* h = c->h_int;
+    h[0] = max_steps; h[1] = break_on_finish ? 1 : 0; h[2] = cap - ss.live;
+    WL_CUDA(cudaMemcpyAsync(c->ds.steps_left, h, 4, cudaMemcpyHostToDevice, st));
+    WL_CUDA(cudaMemcpyAsync(c->ds.brk, h + 1, 8, cudaMemcpyHostToDevice, st));
+    WL_CUDA(cudaEventRecord(c->ev0, st));
+    if (ss.use_graph) {
+      long kernels = 0;
+      cudaGraphExec_t exec = decode_graph(c, "s", cap, ss.Kr, ss.K, ss.so, vi, ss.nsplit, true, &kernels);
+      WL_CUDA(cudaGraphLaunch(exec, st));
+      WL_CUDA(cudaMemcpyAsync(h + 4, c->ds.steps_left, 4, cudaMemcpyDeviceToHost, st));
+      WL_CUDA(cudaMemcpyAsync(h + 8, c->ds.done, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
+      WL_CUDA(cudaEventRecord(c->ev1, st));
+      WL_CUDA(cudaStreamSynchronize(st));
+      ran = max_steps - h[4];
+      c->graph_launched += kernels * (long)ran;
+    } else {   // graph-less (profiling / bisecting): the same loop condition evaluated on the host after every step
+      for (;;) {
+        decode_step(c, cap, ss.Kr, ss.so, vi, ss.nsplit, false);
+        ++ran;
+        WL_CUDA(cudaMemcpyAsync(h + 5, c->ds.n_done, 4, cudaMemcpyDeviceToHost, st));
+        WL_CUDA(cudaStreamSynchronize(st));
+        if (ran >= max_steps || h[5] >= cap || (break_on_finish && h[5] > h[2])) break;
+      }
+      WL_CUDA(cudaMemcpyAsync(h + 8, c->ds.done, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
+      WL_CUDA(cudaEventRecord(c->ev1, st));
+      WL_CUDA(cudaStreamSynchronize(st));
+    }
+    WL_CUDA(cudaEventElapsedTime(&c->last_ms[2], c->ev0, c->ev1));
+    for (int b = 0; b < cap; ++b)
+      if (ss.used[b] && !ss.finished[b] && h[8 + b]) { ss.finished[b] = 1; ss.live -= 1; }
+    ss.steps += ran;
+    ss.runs += 1;
+  }
+  for (int b = 0; b < cap; ++b) done_out[b] = (ss.used[b] && ss.finished[b]) ? 1 : 0;
+  if (steps_ran) *steps_ran = ran;
+  API_END(c)
+}
+
+extern "C" int wl_session_collect(wl_ctx* c, int32_t index, int32_t* out_ids, int32_t* out_len, float* out_score, float* out_no_speech,
+                                  int32_t* out_steps) {
+  API_BEGIN(c)
+  wl_ctx::Session& ss = c->sess;
+  WL_CHECK(ss.open, WL_ERR_STATE, "wl_session_collect: no open session");
+  WL_CHECK(index >= 0 && index < ss.cap && out_ids && out_len && out_score, WL_ERR_ARG, "wl_session_collect: bad arguments");
+  WL_CHECK(ss.used[index] && ss.finished[index], WL_ERR_STATE, "wl_session_collect: stream index %d has not finished", index);
+  const DecodeState& s = ss.ds;
+  cudaStream_t st = c->st;
+  ensure_host(c, (size_t)MAX_HYPS * (T_MAX + 2) + 16, MAX_HYPS + 2);
+  int* h_cnt = c->h_int;
+  int* h_steps = h_cnt + 1;
+  int* h_len = h_cnt + 8;
+  int* h_tok = h_len + MAX_HYPS;
+  float* h_cum = c->h_flt;
+  float* h_ns = h_cum + MAX_HYPS;
+  WL_CUDA(cudaMemcpyAsync(h_cnt, s.hyp_count + index, 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_steps, s.steps_run + index, 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_len, s.hyp_len + (size_t)index * MAX_HYPS, MAX_HYPS * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_tok, s.hyp_tok + (size_t)index * MAX_HYPS * T_MAX, (size_t)MAX_HYPS * T_MAX * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_cum, s.hyp_cum + (size_t)index * MAX_HYPS, MAX_HYPS * 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaMemcpyAsync(h_ns, s.no_speech + index, 4, cudaMemcpyDeviceToHost, st));
+  WL_CUDA(cudaStreamSynchronize(st));
+  emit_hyps(ss.NH, ss.length_penalty, h_cnt[0], h_len, h_cum, h_tok, out_ids, out_len, out_score);
+  if (out_no_speech) *out_no_speech = h_ns[0];
+  if (out_steps) *out_steps = h_steps[0];
+  ss.used[index] = 0;
+  ss.finished[index] = 0;
+  API_END(c)
+}
+
+extern "C" int wl_session_close(wl_ctx* c) {
+  API_BEGIN(c)
+  wl_ctx::Session& ss = c->sess;
+  if (ss.open) {   // streams still in flight are dropped: their indices go idle again
+    const int cap = ss.cap;
+    std::vector<int> ones(cap, 1);
+    const int nd = cap;
+    WL_CUDA(cudaMemcpy(ss.ds.done, ones.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    WL_CUDA(cudaMemset(ss.ds.active, 0, (size_t)cap * ss.Kr * 4));
+    WL_CUDA(cudaMemcpy(ss.ds.n_done, &nd, 4, cudaMemcpyHostToDevice));
+    ss.used.assign(cap, 0);
+    ss.finished.assign(cap, 0);
+    ss.live = 0;
+    ss.open = false;
   }
   API_END(c)
 }

@@ -93,6 +93,8 @@ struct DecodeState {
   int* n_done;       // [1] number of finished streams
   int* steps_left;   // [1] decode steps the device-side loop may still run (conditional WHILE graph)
   unsigned* seed;    // [1] sampling seed of this generate call (device scalar: the captured graph does not depend on it)
+  int* brk;          // [2] decode sessions (step-level admission): [0] != 0 -> the device-side loop also ends as soon as a
+                     //   stream finishes (so the host can hand its result out and refill the index); [1] = n_done at launch
   // teacher-forced mode (detect_language / align / logits test hook)
   int* force_len;    // [B] 0 = normal search; >0 = feed prompt only, then stop
   float* force_prob; // [B][T_MAX] P(prompt[i+1] | prompt[..i]) in teacher-forced mode
@@ -143,7 +145,10 @@ void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalH
 
 // initialise the state for a generate call (prompts already uploaded).  prefilled = 1: positions 0 .. P-2 of every prompt
 // are already in the self-attention cache (K8 batched prefill): start at the last prompt token.
-void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled = 0);
+// index != null (device, B entries): initialise only those state indices of a running decode session -- their `done`
+// flag was 1 and is counted in n_done, which drops by one per admitted stream instead of being reset.
+void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled = 0,
+                 const int* index = nullptr);
 
 // ---------------------------------------------------------------------------- K8 batched prefill helpers (prefill.cu)
 void prefill_embed(cudaStream_t st, const int* tok, const int* pos, const int* active, const int* wrow, const __half* emb,

@@ -509,9 +509,11 @@ __global__ void loop_condition_kernel(DecodeState s, cudaGraphConditionalHandle 
   pdl_trigger();
   pdl_wait();
   if (threadIdx.x == 0) {
-    const int left = *s.steps_left - 1;
+    const int left = *s.steps_left - 1, nd = *s.n_done;
     *s.steps_left = left;
-    cudaGraphSetConditional(h, (left > 0 && *s.n_done < B) ? 1u : 0u);
+    bool go = left > 0 && nd < B;
+    if (s.brk[0] != 0 && nd > s.brk[1]) go = false;   // decode session: a stream finished in this step -> back to the host
+    cudaGraphSetConditional(h, go ? 1u : 0u);
   }
 }
 void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalHandle h, int B) {
@@ -521,8 +523,8 @@ void loop_condition(cudaStream_t st, const DecodeState& s, cudaGraphConditionalH
 }
 
 // ============================================================================ init
-__global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v, int prefilled) {
-  const int b = blockIdx.x, tid = threadIdx.x;
+__global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v, int prefilled, const int* __restrict__ index) {
+  const int b = index ? index[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
   const int Kr = o.rows_per_stream, row0 = b * Kr;
   const int P = s.prompt_len[b];
   // token-by-token feeding starts at prompt position 0; after the batched prefill (positions 0 .. P-2 cached in the
@@ -555,12 +557,14 @@ __global__ void decode_init_kernel(DecodeState s, SearchOpts o, VocabIds v, int 
     if (!prefilled) s.no_speech[b] = 0.f;   // the prefill pass zeroes it and, with sot inside the prompt, has already written it
     s.hyp_count[b] = 0;
     s.steps_run[b] = fed0;
-    if (b == 0) *s.n_done = 0;
+    if (index) atomicSub(s.n_done, 1);   // session admission: the index was idle (done = 1, counted)
+    else if (b == 0) *s.n_done = 0;
   }
 }
 
-void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled) {
-  decode_init_kernel<<<B, 32, 0, st>>>(s, o, v, prefilled);
+void decode_init(cudaStream_t st, const DecodeState& s, const SearchOpts& o, const VocabIds& v, int B, int R, int prefilled,
+                 const int* index) {
+  decode_init_kernel<<<B, 32, 0, st>>>(s, o, v, prefilled, index);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }

@@ -388,6 +388,12 @@ class B200Whisper:
         self.last_steps = max((r.steps for r in results), default=0)
         return results
 
+    # ------------------------------------------------------------------ N2: decode session (step-level admission)
+    def open_decode_session(self, capacity: Optional[int] = None, **generate_kwargs) -> "DecodeSession":
+        """A decode loop whose streams come and go independently (``wl_session_*``): same keyword arguments as
+        ``generate`` (``max_length`` is given per stream at admission; sampling options are not accepted)."""
+        return DecodeSession(self, capacity or self.max_streams, **generate_kwargs)
+
     # ------------------------------------------------------------------ ctranslate2.models.Whisper.detect_language
     def detect_language(self, features) -> List[List[Tuple[str, float]]]:
         if not self.is_multilingual:
@@ -493,3 +499,139 @@ class B200Whisper:
                                        bp, _lib.ptr(c, C.c_float), M, N, K, Z, int(transposed_store), int(gelu), int(use_simt))
             _lib.check(self.lib, self.ctx, rc, "wl_test_gemm")
         return c
+
+
+class DecodeSession:
+    """Step-level continuous batching on one engine context (``include/wlb200.h``: ``wl_session_*``).
+
+    The reference's batcher runs a batch to completion before it looks at the queue again
+    (whisper_live/batch_inference.py:155-187); here a stream is admitted at any token-step boundary into a free index
+    of the running decode loop, and a finished stream is collected while the others keep decoding:
+
+        sess = engine.open_decode_session(beam_size=5, suppress_tokens=...)
+        idx = sess.admit([enc_a, enc_b], [prompt_a, prompt_b], [448, 448])
+        while sess.live:
+            for i in sess.run(max_steps=16):        # returns early when a stream finishes
+                result = sess.collect(i)            # WhisperGenerationResult, the index is free again
+            ... admit whoever arrived meanwhile ...
+
+    One-shot engine calls (``encode``, ``generate`` for a temperature-fallback retry, ``align``, ``detect_language``)
+    may be interleaved between two ``run`` calls: the session owns its decode state and self-attention cache."""
+
+    def __init__(self, engine: B200Whisper, capacity: int, *, beam_size: int = 5, patience: float = 1, num_hypotheses: int = 1,
+                 length_penalty: float = 1, repetition_penalty: float = 1, no_repeat_ngram_size: int = 0,
+                 max_initial_timestamp_index: int = 50, suppress_blank: bool = True,
+                 suppress_tokens: Optional[Sequence[int]] = (-1,), sampling_topk: int = 1, sampling_temperature: float = 1,
+                 return_scores: bool = False, return_no_speech_prob: bool = False, max_length: int = T_MAX, **_ignored):
+        if repetition_penalty != 1 or no_repeat_ngram_size != 0:
+            raise NotImplementedError("repetition_penalty / no_repeat_ngram_size other than the reference's 1 / 0")
+        if int(beam_size) == 1 and sampling_topk != 1 and sampling_temperature > 0:
+            raise ValueError("a decode session does not sample: run temperature-fallback retries through generate()")
+        self.engine = engine
+        self.capacity = int(capacity)
+        self.num_hypotheses = int(num_hypotheses)
+        self._sup = np.asarray(sorted({int(t) for t in (suppress_tokens or ()) if t >= 0}), dtype=np.int32)
+        self._opts = _lib.WlGenOpts(
+            beam_size=int(beam_size), patience=float(patience), num_hypotheses=self.num_hypotheses,
+            length_penalty=float(length_penalty), max_length=int(max_length), suppress_blank=int(bool(suppress_blank)),
+            max_initial_timestamp_index=int(max_initial_timestamp_index), sampling_topk=1, sampling_temperature=1.0, seed=0,
+            suppress_tokens=_lib.ptr(self._sup, C.c_int32) if len(self._sup) else None, n_suppress=len(self._sup),
+            use_cuda_graph=int(engine.use_cuda_graph), max_length_per_stream=None, prefill=1)
+        self._held: Dict[int, EncoderOutput] = {}     # index -> the encoder view its stream decodes against
+        self._finished: List[int] = []
+        self.steps = 0
+        self.runs = 0
+        self.closed = False
+        with engine._lock:
+            rc = engine.lib.wl_session_open(engine.ctx, C.byref(self._opts), self.capacity)
+            _lib.check(engine.lib, engine.ctx, rc, "wl_session_open")
+
+    # -- bookkeeping -------------------------------------------------------------------------------
+    @property
+    def live(self) -> int:
+        """streams admitted and not yet collected"""
+        return len(self._held)
+
+    def free_indices(self) -> List[int]:
+        return [i for i in range(self.capacity) if i not in self._held]
+
+    # -- admission ---------------------------------------------------------------------------------
+    def admit(self, features: Sequence[EncoderOutput], prompts: Sequence[Sequence[int]], max_lengths: Sequence[int],
+              indices: Optional[Sequence[int]] = None) -> List[int]:
+        """Admit one stream per (single-stream encoder view, prompt, max_length); returns the indices they decode in."""
+        n = len(prompts)
+        if n == 0:
+            return []
+        if len(features) != n or len(max_lengths) != n:
+            raise ValueError("admit: features / prompts / max_lengths differ in length")
+        free = self.free_indices()
+        if indices is None:
+            if n > len(free):
+                raise RuntimeError(f"admit: {n} streams for {len(free)} free indices")
+            indices = free[:n]
+        slots = []
+        for f in features:
+            if not isinstance(f, EncoderOutput) or len(f) != 1:
+                raise TypeError("admit: every stream needs its own single-stream EncoderOutput view")
+            slots.append(int(f.slots[0]))
+        ps = [list(map(int, p)) for p in prompts]
+        off = np.zeros(n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(p) for p in ps])
+        flat = np.asarray([t for p in ps for t in p], dtype=np.int32)
+        idx = np.asarray(list(indices), dtype=np.int32)
+        sl = np.asarray(slots, dtype=np.int32)
+        ml = np.asarray(list(max_lengths), dtype=np.int32)
+        eng = self.engine
+        with eng._lock:
+            rc = eng.lib.wl_session_admit(eng.ctx, n, _lib.ptr(idx, C.c_int32), _lib.ptr(sl, C.c_int32), _lib.ptr(flat, C.c_int32),
+                                          _lib.ptr(off, C.c_int32), _lib.ptr(ml, C.c_int32))
+            _lib.check(eng.lib, eng.ctx, rc, "wl_session_admit")
+        for i, f in zip(idx.tolist(), features):
+            self._held[i] = f
+        return idx.tolist()
+
+    # -- the token loop ----------------------------------------------------------------------------
+    def run(self, max_steps: int = 16, break_on_finish: bool = True) -> List[int]:
+        """Up to ``max_steps`` token steps over every admitted stream; returns the indices that are finished and waiting
+        to be collected."""
+        eng = self.engine
+        done = np.zeros(self.capacity, dtype=np.int32)
+        ran = C.c_int32(0)
+        with eng._lock:
+            rc = eng.lib.wl_session_run(eng.ctx, int(max_steps), int(bool(break_on_finish)), _lib.ptr(done, C.c_int32), C.byref(ran))
+            _lib.check(eng.lib, eng.ctx, rc, "wl_session_run")
+        self.steps += int(ran.value)
+        self.runs += 1
+        self.last_steps = int(ran.value)
+        self._finished = [i for i in range(self.capacity) if done[i]]
+        return list(self._finished)
+
+    def collect(self, index: int) -> WhisperGenerationResult:
+        eng = self.engine
+        NH = self.num_hypotheses
+        ids = np.zeros((NH, T_MAX), dtype=np.int32)
+        lens = np.zeros(NH, dtype=np.int32)
+        score = np.zeros(NH, dtype=np.float32)
+        nsp = C.c_float(0.0)
+        steps = C.c_int32(0)
+        with eng._lock:
+            rc = eng.lib.wl_session_collect(eng.ctx, int(index), _lib.ptr(ids, C.c_int32), _lib.ptr(lens, C.c_int32),
+                                            _lib.ptr(score, C.c_float), C.byref(nsp), C.byref(steps))
+            _lib.check(eng.lib, eng.ctx, rc, "wl_session_collect")
+        self._held.pop(int(index), None)
+        seqs, scs = [], []
+        for h in range(NH):
+            if lens[h] >= 0:
+                seqs.append(ids[h, :lens[h]].tolist())
+                scs.append(float(score[h]))
+        return WhisperGenerationResult(seqs, scs, float(nsp.value), int(steps.value))
+
+    def close(self) -> None:
+        if self.closed:
+            return
+        self.closed = True
+        eng = self.engine
+        with eng._lock:
+            rc = eng.lib.wl_session_close(eng.ctx)
+            _lib.check(eng.lib, eng.ctx, rc, "wl_session_close")
+        self._held.clear()

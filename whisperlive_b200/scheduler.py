@@ -10,8 +10,10 @@ the drop-in schema a client thread fills in and waits on); the control flow is d
   alternates ``admit`` (everything that is in the inbox RIGHT NOW, up to the stream capacity) and ``round`` (one device
   round for everything in flight: encode the next windows, one generate call per option set, align, post-process);
 * a stream is answered the moment its last window settles -- it does not wait for the streams it shared rounds with;
-* admission happens between rounds, i.e. between two device calls, not between two batches: a late chunk joins the
-  rounds of the chunks that are already decoding, and the slots of a finished stream are refilled immediately;
+* admission happens between rounds, and a round is at most ``step_tokens`` TOKEN STEPS of the device-side decode loop
+  (``TranscribeSession.step_round`` over the engine's decode session, ``wl_session_*``): a late chunk is encoded,
+  prefilled and joins the loop of the chunks that are already decoding a few token steps after it arrived, and the index
+  of a finished stream is refilled immediately;
 * an engine error fails the streams it touched, never the scheduler (``TranscribeSession`` isolates them).
 
 ``linger_ms`` (default 0) optionally waits for more requests when the engine is idle and a single request arrived --
@@ -58,10 +60,15 @@ class BatchRequest:
 
 
 class RoundScheduler:
-    def __init__(self, transcriber, max_batch_size: int = 8, batch_window_ms: int = 0, linger_ms: Optional[int] = None):
+    def __init__(self, transcriber, max_batch_size: int = 8, batch_window_ms: int = 0, linger_ms: Optional[int] = None,
+                 step_tokens: Optional[int] = 16):
         """``max_batch_size``: streams in flight at once (the engine's ``max_streams``).  ``batch_window_ms`` is accepted
-        for signature compatibility with the reference worker and used as ``linger_ms`` when that is not given."""
+        for signature compatibility with the reference worker and used as ``linger_ms`` when that is not given.
+        ``step_tokens``: token steps per device round (``TranscribeSession.step_round``): the inbox is looked at -- and
+        a finished stream answered -- at least that often, and new streams join the decode loop already running;
+        ``None`` / 0 = window-level rounds (one ``generate`` call run to completion per round)."""
         self.transcriber = transcriber
+        self.step_tokens = int(step_tokens or 0)
         self.capacity = max(1, int(max_batch_size))
         self.linger_s = (batch_window_ms if linger_ms is None else linger_ms) / 1000.0
         self._inbox: Deque[BatchRequest] = collections.deque()
@@ -134,7 +141,10 @@ class RoundScheduler:
             if not in_flight:
                 continue
             try:
-                session.round()
+                if self.step_tokens > 0 and hasattr(session, "step_round"):
+                    session.step_round(self.step_tokens)
+                else:
+                    session.round()
                 self.rounds_run += 1
             except Exception as e:          # the session isolates per-stream errors; anything else fails what is in flight
                 log.error("round failed: %s", e)

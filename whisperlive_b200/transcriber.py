@@ -495,6 +495,11 @@ class TranscribeSession:
         self.entries: List[_Entry] = []
         self._next_handle = 0
         self.rounds = 0
+        # step-level rounds (step_round): the engine's decode session, its option key, index -> entry of the streams in it
+        self._dsess = None
+        self._dsess_key: Optional[str] = None
+        self._running: Dict[int, _Entry] = {}
+        self.admitted_steps: List[int] = []   # session step count at each admission (tests: > 0 = joined a running loop)
 
     # -- admission -------------------------------------------------------------------------------
     def add_job(self, job: _StreamJob, prepared: Optional[dict] = None) -> int:
@@ -585,11 +590,99 @@ class TranscribeSession:
 
     # -- one round ---------------------------------------------------------------------------------
     def round(self) -> None:
+        """Window-level round: encode, ONE generate call per option set run to completion, settle."""
+        self.rounds += 1
+        self._encode_pending()
+        settled = self._generate_groups([e for e in self.entries if e.state == "decode"])
+        self._settle(settled)
+
+    def step_round(self, max_steps: int = 16) -> None:
+        """Token-step-level round (N2): the streams whose windows are ready JOIN the decode loop that is already running
+        (``engine.open_decode_session``), the loop advances by at most ``max_steps`` token steps -- or until some stream
+        finishes -- and whatever finished is settled while the others stay in the loop.  A stream that arrives while 31
+        others are in the middle of a 100-token decode starts decoding a few token steps later, and is answered when ITS
+        last window settles.  Falls back to ``round()`` on engines without decode sessions.
+
+        What stays on the one-shot path: sampling retries of the temperature ladder (their noise is keyed per call),
+        streams whose search options differ from the open session's while it is busy wait for it to drain."""
         m = self.m
+        if not hasattr(m.model, "open_decode_session"):
+            return self.round()
         tm = getattr(m, "last_timing", None) or {}
         self.rounds += 1
+        self._encode_pending()
+        one_shot: List[_Entry] = []
+        joining: List[Tuple[_Entry, int]] = []
+        waiting = [e for e in self.entries if e.state == "decode"]
+        for e in waiting:
+            try:
+                kw = e.job.generate_kwargs()
+            except Exception as ex:
+                self._fail(e, ex)
+                continue
+            if kw.get("beam_size", 1) == 1 and kw.get("sampling_topk", 1) != 1 and kw.get("sampling_temperature", 0) > 0:
+                one_shot.append(e)
+                continue
+            key = json.dumps({a: v for a, v in kw.items() if a != "max_length"}, sort_keys=True, default=list)
+            ds = self._dsess
+            if ds is None or (key != self._dsess_key and ds.live == 0 and not joining):
+                if ds is not None:
+                    ds.close()
+                skw = {a: v for a, v in kw.items() if a != "max_length"}
+                ds = self._dsess = m.model.open_decode_session(**skw)
+                self._dsess_key = key
+            if key != self._dsess_key or len(joining) >= len(ds.free_indices()):
+                continue                                   # next step_round: the loop has to drain / free an index first
+            joining.append((e, kw["max_length"]))
+        if joining:                                        # ONE admission = one batched prefill pass for all of them
+            ds = self._dsess
+            try:
+                idxs = ds.admit([e.job.enc for e, _ in joining], [e.job.prompt for e, _ in joining], [ml for _, ml in joining])
+            except Exception as ex:
+                for e, _ in joining:
+                    self._fail(e, ex)
+                idxs = []
+            for idx, (e, _) in zip(idxs, joining):
+                e.state = "running"
+                self._running[idx] = e
+                self.admitted_steps.append(getattr(ds, "steps", 0))
+        settled = self._generate_groups(one_shot)
+        ds = self._dsess
+        if ds is not None and ds.live:
+            t0 = time.perf_counter()
+            try:
+                finished = ds.run(max_steps=max_steps, break_on_finish=True)
+            except Exception as ex:
+                for e in list(self._running.values()):
+                    self._fail(e, ex)
+                self._running.clear()
+                self._dsess = None
+                finished = []
+            tm["generate"] = tm.get("generate", 0.0) + time.perf_counter() - t0
+            for idx in finished:
+                e = self._running.pop(idx)
+                try:
+                    r = ds.collect(idx)
+                    if e.job.accept(r):
+                        settled.append(e)
+                    else:
+                        e.state = "decode"                 # next rung of the temperature ladder
+                except Exception as ex:
+                    self._fail(e, ex)
+        self._settle(settled)
+
+    def close(self) -> None:
+        if self._dsess is not None:
+            self._dsess.close()
+            self._dsess = None
+
+    # -- the three parts of a round -----------------------------------------------------------------
+    def _encode_pending(self) -> None:
+        """Encode the next 30 s window of every stream that needs one (groups of at most ``engine.max_streams``, never
+        more windows than the encoder slot pool has free); language id + prompt for each."""
+        m = self.m
+        tm = getattr(m, "last_timing", None) or {}
         cap = int(getattr(m.model, "max_streams", 0) or 0) or max(1, len(self.entries))
-        # 1. encode
         need = [e for e in self.entries if e.state == "window"]
         free = getattr(m.model, "free_slots", None)
         if callable(free):
@@ -618,10 +711,15 @@ class TranscribeSession:
                     e.state = "decode"
                 except Exception as ex:
                     self._fail(e, ex)
-        # 2. one generate call per option set
+
+    def _generate_groups(self, entries: List[_Entry]) -> List[_Entry]:
+        """ONE run-to-completion ``generate`` call per distinct option set over ``entries``; returns those whose window
+        settled (the others stay in "decode" for the next rung of the temperature ladder)."""
+        m = self.m
+        tm = getattr(m, "last_timing", None) or {}
         groups: Dict[str, List[_Entry]] = {}
         kwargs = {}
-        for e in [e for e in self.entries if e.state == "decode"]:
+        for e in entries:
             try:
                 kw = e.job.generate_kwargs()
             except Exception as ex:
@@ -650,7 +748,13 @@ class TranscribeSession:
                     settled.append(e)
             tm["generate"] = tm.get("generate", 0.0) + t1 - t0
             tm["host_decode"] = tm.get("host_decode", 0.0) + time.perf_counter() - t1
-        # 3. alignment + window post-processing of what settled
+        return settled
+
+    def _settle(self, settled: List[_Entry]) -> None:
+        """Batched word alignment + window post-processing of the streams whose decode settled; each moves on to its
+        next window or is done."""
+        m = self.m
+        tm = getattr(m, "last_timing", None) or {}
         t0 = time.perf_counter()
         try:
             m._align_entries(settled)
