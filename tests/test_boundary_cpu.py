@@ -330,6 +330,53 @@ def test_multi_device_model_fans_out_and_keeps_order():
     m.close()
 
 
+def test_multi_device_session_places_and_steps_every_device():
+    """The scheduler-facing session of a multi-GPU model: streams go to the least-loaded device and stay there, the
+    rounds of all devices run, every stream comes back under its own handle with the single-device result."""
+    from whisperlive_b200 import synth
+    from whisperlive_b200.parallel import MultiDeviceWhisperModel
+    from whisperlive_b200.scheduler import BatchRequest, RoundScheduler
+    torch.set_num_threads(2)
+    models = [_oracle_model(), _oracle_model()]
+    md = MultiDeviceWhisperModel("micro.en", device_index=[0, 1], models=models)
+    waves = [synth.speech_like(3.0 + i, seed=80 + i) for i in range(3)]
+    kw = dict(temperature=[0.0], log_prob_threshold=None, language="en", vad_filter=False)
+    ref = models[0].transcribe_batch(waves, [kw] * 3)
+    sess = md.open_session()
+    h01 = sess.add_streams(waves[:2], [kw] * 2)
+    sess.step_round(4)
+    h2 = sess.add_streams(waves[2:], [kw])               # joins while the first two are decoding
+    assert sess.placed[:2] == [0, 1] and sess.placed[2] in (0, 1)
+    got, guard = {}, 0
+    while sess.pending():
+        sess.step_round(4)
+        for e in sess.pop_finished():
+            got[e.handle] = sess.result_of(e)
+        guard += 1
+        assert guard < 500
+    for e in sess.pop_finished():
+        got[e.handle] = sess.result_of(e)
+    sess.close()
+    for h, (segs, _info) in zip(h01 + h2, ref):
+        assert [s.tokens for s in got[h][0]] == [s.tokens for s in segs]
+
+    class Req(BatchRequest):
+        def kwargs(self):
+            return dict(kw)
+    sch = RoundScheduler(md, max_batch_size=4, step_tokens=4)
+    sch.start()
+    try:
+        reqs = [Req(audio=w) for w in waves]
+        for r in reqs:
+            sch.submit(r)
+        assert all(r.future.wait(240) for r in reqs)
+    finally:
+        sch.stop()
+        md.close()
+    for r, (segs, _info) in zip(reqs, ref):
+        assert r.error is None and [s.tokens for s in r.result] == [s.tokens for s in segs]
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside ours) works without a GPU and prints one JSON line
     with the contract's keys; a tiny architecture keeps it to seconds."""

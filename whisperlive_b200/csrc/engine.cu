@@ -826,6 +826,12 @@ void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* prob
                         int layer, int B, int rows_per_stream, int H);
 }
 
+// WLB200_XA_PREFETCH (read at every call, part of the graph key: a sweep can change it inside one process)
+static int xa_prefetch_streams() {
+  const char* e = getenv("WLB200_XA_PREFETCH");
+  return e ? atoi(e) : 0;
+}
+
 static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const VocabIds& vi, int nsplit, bool align_mode) {
   const int d = c->d, H = c->H, ff = 4 * c->d, R = B * Kr;
   cudaStream_t st = c->st;
@@ -926,9 +932,21 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
     if (use_wg) wgemm(st, W, n_out, K, X, R, bias, mode, of32, of16, 0);
     else cgemm(st, W, n_out, K, X, R, bias, mode, of32, of16);
   };
+  // WLB200_XA_PREFETCH=n: the layer's first LayerNorm also asks L2 for the encoder K/V of the first n live streams --
+  // the six latency-bound kernels between it and the cross-attention leave HBM idle, the cross-attention is HBM-bound
+  const int xa_pf = xa_prefetch_streams();
+  L2Prefetch pf;
+  if (xa_pf > 0 && !align_mode) {
+    pf.slot = s.slot; pf.done = s.done; pf.B = B;
+    pf.slot_bytes = slot_sz * 2;
+    const long per_region = (pf.slot_bytes + 32 * 1024 - 1) / (32 * 1024);
+    pf.n_streams = (int)std::min<long>(std::min(xa_pf, B), (long)R * 32 / (2 * per_region));   // one 32 KB piece per lane of warp 0
+  }
   for (int l = 0; small && l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
-    layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    pf.k = c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz;
+    pf.v = c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz;
+    layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d, &pf);
     lin(L.w_qkv, 3 * d, d, c->dxn, L.b_qkv, 0, c->part1, nullptr);
     decoder_self_attn(st, s, plain(c->part1), c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
@@ -1284,8 +1302,8 @@ static cudaGraphExec_t decode_graph(wl_ctx* c, const char* tag, int B, int Kr, i
                                     int nsplit, bool loop_graph, long* kernels) {
   cudaStream_t st = c->st;
   char key[160];
-  snprintf(key, sizeof(key), "%s/%d/%d/%d/%d/%d/%d/%d/%08x/%d", tag, B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
-           so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0);
+  snprintf(key, sizeof(key), "%s/%d/%d/%d/%d/%d/%d/%d/%08x/%d/%d", tag, B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
+           so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0, xa_prefetch_streams());
   GraphEntry& ge = c->graphs[key];
   if (!ge.exec) {
     const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count();

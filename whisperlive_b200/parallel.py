@@ -79,8 +79,90 @@ class MultiDeviceWhisperModel:
         self._next = (self._next + 1) % len(self.models)
         return self.models[g].transcribe(audio, **kw)
 
+    def open_session(self) -> "MultiDeviceSession":
+        """What ``RoundScheduler`` drives: one ``TranscribeSession`` per GPU advanced concurrently, so the step-level
+        admission (streams join the running decode loop of THEIR device) works across all of them."""
+        return MultiDeviceSession(self)
+
     def close(self):
         self._pool.shutdown(wait=True)
+
+
+class _PlacedEntry:
+    """A finished stream of one device's session under its scheduler-wide handle."""
+
+    __slots__ = ("handle", "device", "inner")
+
+    def __init__(self, handle, device, inner):
+        self.handle, self.device, self.inner = handle, device, inner
+
+
+class MultiDeviceSession:
+    """``TranscribeSession`` surface (add_streams / round / step_round / pending / pop_finished / result_of) over the
+    per-device sessions of a ``MultiDeviceWhisperModel``.  A new stream goes to the device with the fewest streams in
+    flight (ties: lowest index) and stays there -- its encoder K/V and self-attention cache never move; the rounds of
+    all devices that have work run concurrently on the model's worker threads."""
+
+    def __init__(self, md: MultiDeviceWhisperModel):
+        self.md = md
+        self.sessions = [m.open_session() for m in md.models]
+        self._handles = [dict() for _ in self.sessions]     # per device: local handle -> global handle
+        self._next_handle = 0
+        self.placed: List[int] = []                         # device of every admitted stream, in admission order
+
+    def add_streams(self, audios: Sequence[np.ndarray], per_stream_kwargs: Optional[Sequence[dict]] = None) -> List[int]:
+        n, G = len(audios), len(self.sessions)
+        kws = list(per_stream_kwargs) if per_stream_kwargs is not None else [{} for _ in range(n)]
+        load = [s.pending() for s in self.sessions]
+        place = []
+        for _ in range(n):
+            g = min(range(G), key=lambda k: (load[k], k))
+            load[g] += 1
+            place.append(g)
+        shards = [[i for i in range(n) if place[i] == g] for g in range(G)]
+        futs = {g: self.md._pool.submit(self.sessions[g].add_streams, [audios[i] for i in idx], [kws[i] for i in idx])
+                for g, idx in enumerate(shards) if idx}
+        out = [-1] * n
+        for g, f in futs.items():
+            for i, local in zip(shards[g], f.result()):
+                h = self._next_handle
+                self._next_handle += 1
+                self._handles[g][local] = h
+                out[i] = h
+        self.placed += place
+        return out
+
+    def _each(self, call) -> None:
+        busy = [s for s in self.sessions if s.pending()]
+        futs = [self.md._pool.submit(call, s) for s in busy]
+        errs = [f.exception() for f in futs]
+        for e in errs:
+            if e is not None:
+                raise e
+
+    def round(self) -> None:
+        self._each(lambda s: s.round())
+
+    def step_round(self, max_steps: int = 16) -> None:
+        self._each(lambda s: s.step_round(max_steps) if hasattr(s, "step_round") else s.round())
+
+    def pending(self) -> int:
+        return sum(s.pending() for s in self.sessions)
+
+    def pop_finished(self) -> List[_PlacedEntry]:
+        out = []
+        for g, s in enumerate(self.sessions):
+            for e in s.pop_finished():
+                out.append(_PlacedEntry(self._handles[g].pop(e.handle), g, e))
+        return out
+
+    def result_of(self, entry: _PlacedEntry):
+        return self.sessions[entry.device].result_of(entry.inner)
+
+    def close(self) -> None:
+        for s in self.sessions:
+            if hasattr(s, "close"):
+                s.close()
 
 
 # ------------------------------------------------------------------------------------------ one process per GPU

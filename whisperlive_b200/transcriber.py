@@ -656,6 +656,10 @@ class TranscribeSession:
                 for e in list(self._running.values()):
                     self._fail(e, ex)
                 self._running.clear()
+                try:
+                    ds.close()                             # the engine-side session must not keep their indices
+                except Exception:
+                    pass
                 self._dsess = None
                 finished = []
             tm["generate"] = tm.get("generate", 0.0) + time.perf_counter() - t0
