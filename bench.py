@@ -304,6 +304,7 @@ def main():
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    loop_ms, loop_steps = eng.last_device_ms(2), getattr(eng, "last_steps", None)   # the last e2e step's decode loop
     # ---- streaming phase: staggered arrivals through the product scheduler (N=1 rank-local; reported, not the headline)
     streaming = None
     if not args.no_streaming and not args.word_timestamps:
@@ -329,7 +330,7 @@ def main():
         d2h += n_local * ((448 + 1500 + 2) * 8 + 448 * 4)
 
     # ---- roofline of the dominant kernel (cross-attention K/V streaming), measured live
-    roof = dominant_kernel_roofline(eng, dims, n_local, args.beam, feats_cache)
+    roof = dominant_kernel_roofline(eng, dims, n_local, args.beam, feats_cache, loop_ms, loop_steps)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -422,7 +423,7 @@ def streaming_latency(model, waves, kws, durs, batch_step_s: float, load: float,
                     "through the product scheduler (streams join the running device-side decode loop)"}
 
 
-def dominant_kernel_roofline(eng, dims, n_streams, beam, feats_cache):
+def dominant_kernel_roofline(eng, dims, n_streams, beam, feats_cache, loop_ms, loop_steps):
     """Roofline of the dominant kernel, decoder cross-attention (K11, cross_attn_kernel): one launch streams the
     encoder K and V of every live stream for one layer, 2 * 1500 * d_model fp16 values per stream (DESIGN.md
     section 4) -- HBM-bound.  Its launch duration is measured live: a short graph-less generate pass over the
@@ -437,8 +438,7 @@ def dominant_kernel_roofline(eng, dims, n_streams, beam, feats_cache):
     which = "measured burst copy bandwidth (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     d, L, V = dims.d_model, dims.dec_layers, dims.vocab
     # whole decode loop of the last timed generate call
-    steps = eng.last_steps if hasattr(eng, "last_steps") else None
-    ms = eng.last_device_ms(2)
+    steps, ms = loop_steps, loop_ms
     step_info = None
     if steps and ms > 0:
         w_step = (14 * d * d * L + V * d) * 2

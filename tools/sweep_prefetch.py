@@ -14,6 +14,7 @@ ap.add_argument("--streams", default="32")
 ap.add_argument("--tokens", type=int, default=60)
 ap.add_argument("--beam", type=int, default=4)
 ap.add_argument("--values", default="0,4,8,12,16")
+ap.add_argument("--cgemm", default="0", help="comma list of WLB200_CGEMM values to cross with the prefetch values")
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 
@@ -33,8 +34,9 @@ enc_all = eng.encode(np.stack([f[:, :3000] for f in feats]))
 for S in [int(x) for x in a.streams.split(",")]:
     enc = enc_all.select(list(range(S)))
     base = None
-    for v in [int(x) for x in a.values.split(",")]:
+    for cg, v in [(cg, int(x)) for cg in a.cgemm.split(",") for x in a.values.split(",")]:
         os.environ["WLB200_XA_PREFETCH"] = str(v)
+        os.environ["WLB200_CGEMM"] = cg
         ms = []
         for rep in range(a.reps + 1):
             out = eng.generate(enc, [sot] * S, beam_size=a.beam, suppress_tokens=[eng.eot], suppress_blank=False, max_length=2 * a.tokens)
@@ -42,4 +44,4 @@ for S in [int(x) for x in a.streams.split(",")]:
                 ms.append(eng.last_device_ms(2) / max(o.steps for o in out))
         m = float(np.median(ms))
         base = base or m
-        print(f"streams {S:3d} prefetch {v:3d}: {m:.4f} ms per token step ({m / base:.3f} of prefetch 0)  runs {[round(x, 4) for x in ms]}", flush=True)
+        print(f"streams {S:3d} cgemm {cg} prefetch {v:3d}: {m:.4f} ms per token step ({m / base:.3f} of the first row)  runs {[round(x, 4) for x in ms]}", flush=True)

@@ -826,10 +826,18 @@ void gather_align_probs(cudaStream_t st, const DecodeState& s, const float* prob
                         int layer, int B, int rows_per_stream, int H);
 }
 
-// WLB200_XA_PREFETCH (read at every call, part of the graph key: a sweep can change it inside one process)
+// Switches that are read at every call and are part of the graph key, so that one process can sweep them
+// (tools/sweep_prefetch.py): WLB200_XA_PREFETCH, WLB200_CGEMM
 static int xa_prefetch_streams() {
   const char* e = getenv("WLB200_XA_PREFETCH");
   return e ? atoi(e) : 0;
+}
+// Measured on B200 (bench.py, large-v3, beam 4): the cluster split-K GEMM (cgemm) made the token step SLOWER than split-K
+// partials summed by the consumers -- 3.81 vs 2.87 ms at 32 streams, 262 vs 206 ms per 8-stream batch -- so it is off by
+// default; what it costs is the serial DSMEM reduction and two cluster barriers after the MMAs.
+static bool cgemm_enabled() {
+  const char* e = getenv("WLB200_CGEMM");
+  return e ? atoi(e) != 0 : false;
 }
 
 static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const VocabIds& vi, int nsplit, bool align_mode) {
@@ -922,9 +930,9 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   // 17..32 take the tcgen05 path below until the K split moves into a cluster)
   static const int wg_max_rows = [] { const char* e = getenv("WLB200_WGEMM_ROWS"); return e ? atoi(e) : 16; }();
   const bool use_wg = wg_env && R <= wg_max_rows && wgemm_supported(R, d) && wgemm_supported(R, ff);
-  // Above that: cgemm, the tcgen05 pipeline with the K split inside a cluster (dec_gemm.cu) -- same fused epilogues, so
-  // the layer is the same 12 launches at every batch size.  WLB200_CGEMM=0 falls back to split-K partials (13 launches).
-  static const bool cg_env = [] { const char* e = getenv("WLB200_CGEMM"); return e ? atoi(e) != 0 : true; }();
+  // Above that: split-K partials summed by the consumers (13 launches per layer), or with WLB200_CGEMM=1 cgemm, the
+  // tcgen05 pipeline with the K split inside a cluster (dec_gemm.cu) -- same fused epilogues as wgemm, 12 launches.
+  const bool cg_env = cgemm_enabled();
   const bool small = !simt_env && !fuse && (use_wg || cg_env);
   auto plain = [](const float* ptr) { PartialSrc ps; ps.ptr = ptr; ps.nsplit = 1; ps.stride = 0; ps.bias = nullptr; return ps; };
   // mode 0: out_f32 = X W^T + bias; 1: out_f32 += X W^T + bias; 2: out_f16 = gelu(X W^T + bias)
@@ -969,7 +977,9 @@ static void decode_step(wl_ctx* c, int B, int Kr, const SearchOpts& so, const Vo
   for (int l = 0; !small && l < c->Ld; ++l) {
     const DecLayer& L = c->dec[l];
     const bool last = l + 1 == c->Ld;
-    if (!fuse || l == 0) layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d);
+    pf.k = c->ckv + ((long)l * 2 + 0) * c->NS * slot_sz;
+    pf.v = c->ckv + ((long)l * 2 + 1) * c->NS * slot_sz;
+    if (!fuse || l == 0) layernorm_update_rows(st, c->dx, pending, L.ln1_g, L.ln1_b, c->dxn, R, d, &pf);
     const PartialSrc qkv = part_gemm(L.w_qkv, 3 * d, d, c->dxn, c->part1, L.b_qkv, Post());
     decoder_self_attn(st, s, qkv, c->kcache + (long)l * c->cache_layer_stride, c->vcache + (long)l * c->cache_layer_stride,
                       c->cache_row_stride, c->datt, R, H, d);
@@ -1303,7 +1313,7 @@ static cudaGraphExec_t decode_graph(wl_ctx* c, const char* tag, int B, int Kr, i
   cudaStream_t st = c->st;
   char key[160];
   snprintf(key, sizeof(key), "%s/%d/%d/%d/%d/%d/%d/%d/%08x/%d/%d", tag, B, Kr, K, so.max_cand, so.suppress_blank, so.max_initial_ts,
-           so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0, xa_prefetch_streams());
+           so.sampling, *(const unsigned*)&so.temperature, loop_graph ? 1 : 0, xa_prefetch_streams() * 2 + (cgemm_enabled() ? 1 : 0));
   GraphEntry& ge = c->graphs[key];
   if (!ge.exec) {
     const long before = gemm_launch_count() + dec_gemm_launch_count() + wgemm_launch_count() + cgemm_launch_count() + other_launch_count();
