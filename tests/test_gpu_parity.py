@@ -607,18 +607,9 @@ def test_align_matches_oracle():
 
 
 # --------------------------------------------------------------------------------------- end to end (Boundary B)
-def test_transcribe_end_to_end_matches_oracle_pipeline():
-    from whisperlive_b200.feature_extractor import FeatureExtractor
-    from whisperlive_b200.transcriber import B200WhisperModel
-    eng, orc = engine("micro.en", seed=0)
-    dims = eng.dims
-    hf = build_synthetic_tokenizer(dims.vocab)
-    gpu = B200WhisperModel("micro.en", engine=eng, hf_tokenizer=hf, feature_extractor=FeatureExtractor(eng, dims.n_mels))
-    cpu = B200WhisperModel("micro.en", engine=orc, hf_tokenizer=hf, feature_extractor=OracleFeatureExtractor(dims.n_mels))
-    audios = [synth.speech_like(6.0, seed=1), synth.speech_like(33.0, seed=2)]
-    kw = dict(temperature=[0.0], log_prob_threshold=None, beam_size=5)
-    got = gpu.transcribe_batch(audios, [kw, kw])
-    ref = [cpu.transcribe(a, **kw) for a in audios]
+def _compare_transcripts(got, ref):
+    """(segments, info) pairs of the CUDA transcriber against the oracle-engine transcriber: identical, or identical up to
+    an explained decode divergence (near-tie) after which only the average log-probs are comparable."""
     for (gs, gi), (rs, ri) in zip(got, ref):
         assert gi.language == ri.language and gi.duration == ri.duration
         same = [a.tokens == b.tokens for a, b in zip(gs, rs)]
@@ -643,6 +634,22 @@ def test_transcribe_end_to_end_matches_oracle_pipeline():
             # and the divergence itself is a near-tie: the two transcripts' average log-probs agree
             if first < min(len(gs), len(rs)):
                 assert gs[first].avg_logprob == pytest.approx(rs[first].avg_logprob, abs=0.3)
+
+
+
+def test_transcribe_end_to_end_matches_oracle_pipeline():
+    from whisperlive_b200.feature_extractor import FeatureExtractor
+    from whisperlive_b200.transcriber import B200WhisperModel
+    eng, orc = engine("micro.en", seed=0)
+    dims = eng.dims
+    hf = build_synthetic_tokenizer(dims.vocab)
+    gpu = B200WhisperModel("micro.en", engine=eng, hf_tokenizer=hf, feature_extractor=FeatureExtractor(eng, dims.n_mels))
+    cpu = B200WhisperModel("micro.en", engine=orc, hf_tokenizer=hf, feature_extractor=OracleFeatureExtractor(dims.n_mels))
+    audios = [synth.speech_like(6.0, seed=1), synth.speech_like(33.0, seed=2)]
+    kw = dict(temperature=[0.0], log_prob_threshold=None, beam_size=5)
+    got = gpu.transcribe_batch(audios, [kw, kw])
+    ref = [cpu.transcribe(a, **kw) for a in audios]
+    _compare_transcripts(got, ref)
 
 
 # --------------------------------------------------------------------------------------- BASELINE configs at full size
@@ -841,6 +848,33 @@ def test_full_size_large_v3_single_stream():
     rescored = _oracle_rescore(orc, oenc, 0, sot_seq, a.sequences_ids[0], kw)
     print(f"generate large-v3 beam 4: {len(a.sequences_ids[0])} tokens, engine score {a.scores[0]:.4f}, oracle score of the same tokens {rescored:.4f}")
     assert abs(rescored - a.scores[0]) < 0.02                                    # measured: 0.0013
+
+
+# --------------------------------------------------------------------------------------- BASELINE config 1 input
+def test_config1_jfk_chunk():
+    """BASELINE config 1's input -- the reference's only audio asset, assets/jfk.flac (its WER test, tests/test_server.py:
+    92-118), decoded + resampled to 16 kHz by tests/golden/make_golden_jfk.py into a committed fixture: 176 000 samples of
+    REAL speech (everything else here is synthetic).  K1 on it against the oracle, then the whole single-client path at
+    the tiny.en shape (random weights: no checkpoint offline, so this pins the arithmetic, not the transcript)."""
+    from whisperlive_b200.feature_extractor import FeatureExtractor
+    from whisperlive_b200.transcriber import B200WhisperModel
+    pcm = np.load(os.path.join(os.path.dirname(__file__), "golden", "jfk_16k_i16.npy")).astype(np.float32) / 32768.0
+    assert pcm.shape == (176000,)
+    eng, orc = engine("tiny.en", seed=0)
+    dims = eng.dims
+    feats = FeatureExtractor(eng, dims.n_mels)(pcm)
+    ref = omel.log_mel(pcm, dims.n_mels)
+    assert feats.shape == ref.shape == (dims.n_mels, 1101)
+    print("jfk mel max err", float(np.abs(feats - ref).max()))
+    assert float(np.abs(feats - ref).max()) < 2e-4
+    hf = build_synthetic_tokenizer(dims.vocab)
+    gpu = B200WhisperModel("tiny.en", engine=eng, hf_tokenizer=hf, feature_extractor=FeatureExtractor(eng, dims.n_mels))
+    cpu = B200WhisperModel("tiny.en", engine=orc, hf_tokenizer=hf, feature_extractor=OracleFeatureExtractor(dims.n_mels))
+    kw = dict(temperature=[0.0], log_prob_threshold=None, beam_size=5)       # the live path's defaults (beam 5)
+    got = [gpu.transcribe(pcm, **kw)]
+    refs = [cpu.transcribe(pcm, **kw)]
+    assert got[0][1].duration == pytest.approx(11.0)
+    _compare_transcripts(got, refs)
 
 
 # --------------------------------------------------------------------------------------- N2: decode session

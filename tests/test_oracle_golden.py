@@ -160,3 +160,28 @@ def test_alignment_pipeline_matches_transformers_order():
         w = _median_filter((w - mean) / std, 7).mean(dim=1)[0]
         ti, fi = _dynamic_time_warping(-w[n_start:-1].double().numpy())
         assert got == list(zip(ti.tolist(), fi.tolist()))
+
+
+def test_jfk_fixture_is_the_reference_asset():
+    """tests/golden/jfk_16k_i16.npy = /root/reference/assets/jfk.flac (input of the reference's WER test, tests/test_server.py:
+    92-118; BASELINE config 1) decoded by the self-checking FLAC decoder of make_golden_jfk.py (STREAMINFO MD5 verified) and
+    resampled to 16 kHz mono: 176 000 samples = 11.0 s.  The oracle's K1 on it has the reference feature geometry; when the
+    reference tree is present the fixture is regenerated and must come out identical."""
+    pcm = np.load(os.path.join(GOLD, "jfk_16k_i16.npy"))
+    assert pcm.dtype == np.int16 and pcm.shape == (176000,)
+    assert 20000 < int(np.abs(pcm).max()) < 32768
+    mel = omel.log_mel(pcm.astype(np.float32) / 32768.0, 80)
+    assert mel.shape == (80, 1101) and np.isfinite(mel).all()
+    assert float(mel.max() - mel.min()) <= 2.0 + 1e-6          # (clamp to max - 8, + 4) / 4 -> a dynamic range of at most 2
+    src = "/root/reference/assets/jfk.flac"
+    if os.path.exists(src):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_golden_jfk", os.path.join(GOLD, "make_golden_jfk.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        raw, info = mod.decode_flac(open(src, "rb").read())
+        assert raw.shape == (2, 485100) and info["rate"] == 44100 and info["bps"] == 24
+        from scipy.signal import resample_poly
+        mono = raw.astype(np.float64).mean(axis=0) / float(1 << 23)
+        y = np.clip(np.round(resample_poly(mono, 160, 441) * 32768.0), -32768, 32767).astype(np.int16)
+        np.testing.assert_array_equal(y, pcm)
