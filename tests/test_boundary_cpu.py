@@ -233,9 +233,12 @@ def test_backend_plugin_streams_segments_through_reference_base():
         def close(self):
             self.closed = True
     model = _oracle_model()
-    orig = model.transcribe_batch
-    model.transcribe_batch = lambda audios, kws: orig(audios, [dict(k, temperature=[0.0], beam_size=2, log_prob_threshold=None,
-                                                                         max_new_tokens=24) for k in kws])
+    # keep the CPU oracle cheap: the plugin's requests carry the reference defaults (beam 5, six-rung temperature ladder,
+    # up to 224 new tokens), which is tens of seconds per chunk on the oracle and trips base.py's 30 s request timeout
+    from whisperlive_b200.scheduler import BatchRequest
+    orig_kwargs = BatchRequest.kwargs
+    BatchRequest.kwargs = lambda self: dict(orig_kwargs(self), temperature=[0.0], beam_size=2, log_prob_threshold=None,
+                                            max_new_tokens=24)
     ServeClientB200.MODEL_FACTORY = lambda name: model
     ws = WS()
     try:
@@ -253,6 +256,7 @@ def test_backend_plugin_streams_segments_through_reference_base():
         s0 = segs[0]["segments"][0]
         assert set(s0) >= {"start", "end", "text", "completed"} and segs[0]["uid"] == "u1"
     finally:
+        BatchRequest.kwargs = orig_kwargs
         ServeClientB200.shutdown()
         ServeClientB200.MODEL_FACTORY = None
 
