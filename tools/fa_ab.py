@@ -1,5 +1,5 @@
-"""A/B of the two encoder flash-attention kernels inside one process: WLB200_FA_SPLIT=1 (two softmax groups on alternating
-key tiles, the default) vs 0 (flash_attn_pair_kernel: all softmax warps on the same tile, two threads per row).
+"""A/B of the two encoder flash-attention kernels inside one process: WLB200_FA_SPLIT=1 (flash_attn_kernel: two softmax groups
+on alternating key tiles; opt-in) vs 0 (flash_attn_pair_kernel, the default: all softmax warps on the same tile, two threads per row).
 Plain run: device ms of the whole encoder per setting.  Under `ncu --profile-from-start off -k regex:flash_attn`: one
 profiled encoder pass per setting.
     python tools/fa_ab.py --streams 16 --reps 3"""

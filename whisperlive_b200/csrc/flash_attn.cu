@@ -337,7 +337,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// The previous softmax organisation, kept for A/B measurements (WLB200_FA_SPLIT=0): all 8 softmax warps work on the
+// The DEFAULT kernel (the round-1 / early round-2 softmax organisation): all 8 softmax warps work on the
 // SAME key tile, two threads per query row (64 keys each), per-tile row-max exchange through shared memory.
 __global__ void __launch_bounds__(384, 1)
 flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -608,9 +608,15 @@ void encoder_attention_fused(cudaStream_t st, const __half* qk, const __half* vt
   p.out = out; p.d = d;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid(FA_NT, H, nb);
-  const char* e = getenv("WLB200_FA_SPLIT");   // 1 (default): two softmax groups on alternating key tiles; 0: the pair kernel
-  if (e && atoi(e) == 0) flash_attn_pair_kernel<<<grid, 384, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
-  else flash_attn_kernel<<<grid, 384, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
+  // WLB200_FA_SPLIT=1 selects flash_attn_kernel (two softmax groups on alternating key tiles: 413 vs 502 us per launch at
+  // 16 streams under ncu).  It is NOT the default: its encoder output agrees with the oracle to the same tolerance
+  // (max err 0.013 at large-v3, 0.006 against the pair kernel), but with it two decode-level parity tests fail where they
+  // pass with the pair kernel (tiny beam 5: a pruning gap of 0.52 against the 0.455 allowed; the sampling test: a row
+  // leaves the oracle's at a step whose key margin is 2.4) and the round's GPU budget ended before that was explained.
+  // Parity is the first gate, so the proven kernel runs until it is.
+  const char* e = getenv("WLB200_FA_SPLIT");
+  if (e && atoi(e) != 0) flash_attn_kernel<<<grid, 384, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
+  else flash_attn_pair_kernel<<<grid, 384, FA_SMEM, st>>>(iq.tm, ik.tm, iv.tm, p);
   WL_CUDA(cudaGetLastError());
   note_launch(1);
 }
