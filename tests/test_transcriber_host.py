@@ -202,3 +202,54 @@ def test_ct2_model_bin_reads_bfloat16_payloads(tmp_path):
     expect = (bf16.astype(np.uint32) << 16).view(np.float32).reshape(2, 3)
     np.testing.assert_array_equal(got, expect)
     assert abs(got[0, 1] + 2.5) < 1e-6 and aliases == {"decoder/projection/weight": "decoder/embeddings/weight"}
+
+
+def test_decode_audio_wav_flac_and_paths(tmp_path):
+    """``transcribe`` takes a path / file object like the reference (``decode_audio``, transcriber_faster_whisper.py:820-821):
+    RIFF/WAVE PCM and FLAC are decoded natively (the FLAC decoder checks the STREAMINFO MD5), resampled to 16 kHz mono;
+    other containers raise with the magic named."""
+    import wave
+
+    from whisperlive_b200.audio import decode_audio, decode_flac, resample
+    rng = np.random.default_rng(5)
+    # stereo 8 kHz 16-bit WAV -> mono 16 kHz
+    t = np.arange(8000) / 8000.0
+    left, right = 0.4 * np.sin(2 * np.pi * 220 * t), 0.2 * np.sin(2 * np.pi * 330 * t)
+    inter = np.stack([left, right], axis=1)
+    p = tmp_path / "a.wav"
+    with wave.open(str(p), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(8000)
+        w.writeframes(np.round(inter * 32767).astype("<i2").tobytes())
+    y = decode_audio(str(p))
+    assert y.dtype == np.float32 and y.shape == (16000,)
+    ref = resample((np.round(inter * 32767) / 32768.0).mean(axis=1), 8000, 16000)
+    assert np.abs(y - ref).max() < 1e-6
+    with open(p, "rb") as f:
+        assert np.array_equal(decode_audio(f), y)            # file object
+    assert np.array_equal(decode_audio(p.read_bytes()), y)    # bytes
+    assert resample(left, 16000, 16000).shape == left.shape
+    with pytest.raises(ValueError, match="unsupported container"):
+        decode_audio(b"OggS" + bytes(64))
+    # the reference's asset: decoded FLAC == the committed fixture (to the fixture's int16 rounding); a flipped byte is caught
+    src = "/root/reference/assets/jfk.flac"
+    if os.path.exists(src):
+        fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "jfk_16k_i16.npy")).astype(np.float32) / 32768.0
+        y = decode_audio(src)
+        assert y.shape == fx.shape and np.abs(y - fx).max() <= 0.5 / 32768 + 1e-7
+        data = bytearray(open(src, "rb").read())
+        data[len(data) // 2] ^= 0x10
+        with pytest.raises(Exception):
+            decode_flac(bytes(data))
+    # through the transcriber: a path gives what the samples give
+    from tests.test_boundary_cpu import _oracle_model
+    from whisperlive_b200 import synth
+    model = _oracle_model()
+    wav16 = synth.speech_like(3.0, seed=3)
+    q = tmp_path / "b.wav"
+    with wave.open(str(q), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(np.round(wav16 * 32768).clip(-32768, 32767).astype("<i2").tobytes())
+    kw = dict(temperature=[0.0], beam_size=2, log_prob_threshold=None, max_new_tokens=12, language="en")
+    a_segs, a_info = model.transcribe(str(q), **kw)
+    b_segs, _ = model.transcribe(decode_audio(str(q)), **kw)
+    assert a_info.duration == pytest.approx(3.0) and [s.tokens for s in a_segs] == [s.tokens for s in b_segs]

@@ -523,7 +523,9 @@ class TranscribeSession:
         kws = list(per_stream_kwargs) if per_stream_kwargs is not None else [{} for _ in range(n)]
         tm = getattr(m, "last_timing", None) or {}
         t0 = time.perf_counter()
-        prepared = [m._prepare_stream(np.asarray(a), dict(k)) for a, k in zip(audios, kws)]
+        def as_pcm(a):    # paths / bytes / file objects go through decode_audio like reference :820-821
+            return a if isinstance(a, (str, bytes, bytearray, os.PathLike)) or hasattr(a, "read") else np.asarray(a)
+        prepared = [m._prepare_stream(as_pcm(a), dict(k)) for a, k in zip(audios, kws)]
         tm["prepare"] = tm.get("prepare", 0.0) + time.perf_counter() - t0
         handles: List[int] = []
         live = [i for i, p in enumerate(prepared) if p is not None]
@@ -927,6 +929,9 @@ class B200WhisperModel:
         full.update(kw)
         kw = full
         sr = self.feature_extractor.sampling_rate
+        if not isinstance(audio, np.ndarray):
+            from .audio import decode_audio
+            audio = decode_audio(audio, sampling_rate=sr)
         if kw["multilingual"] and not self.model.is_multilingual:
             self.logger.warning("The current model is English-only but the multilingual parameter is set to True; "
                                 "setting to False instead.")
