@@ -392,6 +392,10 @@ class B200Whisper:
     def open_decode_session(self, capacity: Optional[int] = None, **generate_kwargs) -> "DecodeSession":
         """A decode loop whose streams come and go independently (``wl_session_*``): same keyword arguments as
         ``generate`` (``max_length`` is given per stream at admission; sampling options are not accepted)."""
+        # one session per engine context: whatever an earlier owner left behind (a scheduler stopped mid-decode) is dropped
+        with self._lock:
+            rc = self.lib.wl_session_close(self.ctx)
+            _lib.check(self.lib, self.ctx, rc, "wl_session_close")
         return DecodeSession(self, capacity or self.max_streams, **generate_kwargs)
 
     # ------------------------------------------------------------------ ctranslate2.models.Whisper.detect_language

@@ -123,6 +123,9 @@ class RoundScheduler:
         while True:
             with self._cv:
                 if self._stop and not in_flight and not self._inbox:
+                    close = getattr(session, "close", None)
+                    if close is not None:
+                        close()             # hands the engine's decode session back
                     return
             room = self.capacity - len(in_flight)
             new = self._take(room, block=not in_flight) if room > 0 else []
