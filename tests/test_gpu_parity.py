@@ -195,6 +195,25 @@ def test_encoder_matches_oracle(name):
     assert np.abs(alone[0] - got[1]).max() < 1e-3
 
 
+@pytest.mark.skipif(os.environ.get("WLB200_FA_SPLIT", "0") != "1", reason="diagnostic for the opt-in split flash-attention kernel")
+@pytest.mark.parametrize("name,secs,seeds", [("micro.en", (6.0, 6.0), (1, 2)), ("tiny", (6.0, 6.0, 6.0, 14.0), (1, 2, 3, 7))])
+def test_split_flash_kernel_on_the_decode_tests_inputs(name, secs, seeds):
+    """Round 2 ended with the split flash-attention kernel (WLB200_FA_SPLIT=1) passing every encoder-level check -- all of
+    them on seed-1 weights -- while two decode-level tests on SEED-0 weights fail with it (profiles/flash_ab_r2.md): the
+    sampling test implies a logit error of ~1.9 on an identical prefix, far beyond rounding.  This is the encoder-level
+    check on exactly those tests' weights and inputs; it only runs when the split kernel is selected."""
+    eng, orc = engine(name, seed=0)
+    dims = eng.dims
+    feats = np.stack([feats_for(dims, s, sd) for s, sd in zip(secs, seeds)])
+    got = np.asarray(eng.encode(feats))
+    ref = orc.encode(feats).enc.numpy()
+    for b in range(len(secs)):
+        for t in range(12):
+            sl = slice(t * 128, min(1500, (t + 1) * 128))
+            e = float(np.abs(got[b, sl] - ref[b, sl]).max())
+            assert e < 0.08, (name, "stream", b, "query tile", t, e)
+
+
 def test_encoder_golden_hf():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_hf.npz"))
     for name in ("micro.en", "tiny"):
